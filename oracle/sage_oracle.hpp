@@ -1,0 +1,531 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Never linked into, imported by, or executed from the product path.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may use it.
+//
+// CPU restatement (f64, structurally faithful: per-voxel std::vector storage, per-query candidate copy,
+// sequential map insert) of the SAGE-ICP per-scan registration hot path. The reference itself cannot be
+// compiled here (Eigen, Sophus, oneTBB, tsl::robin_map, PCL absent) so this file IS the
+// checker. PARITY UNPINNED: the reference ships no tests or golden vectors; the oracle is
+// cross-checked by independent numpy/scipy restatements in tests/.
+//
+// Deliberate deviations (documented in DESIGN.md):
+//   * empty 27-neighbourhood => "no correspondence" (the reference reads an uninitialised vector,
+//     core/VoxelHashMap.cpp:80)
+//   * evict_faithful=false gives the "clean" eviction (erase every far voxel); true reproduces the
+//     erase-while-iterating skip of core/VoxelHashMap.cpp:176-184
+//   * tbb::parallel_reduce sites are serial, or OpenMP with static chunks concatenated in thread order.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <tuple>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "robin_table.hpp"
+#include "se3.hpp"
+
+namespace orc {
+
+struct Point4 {  // Eigen::Vector4d = x, y, z, label
+    double x, y, z, l;
+};
+using Cloud = std::vector<Point4>;
+
+inline Vec3 xyz(const Point4 &p) { return {p.x, p.y, p.z}; }
+
+// ---------------------------------------------------------------------------------------------
+// sageConfig — pipeline/sageICP.hpp:39-65 (same field names, same defaults)
+struct Config {
+    std::vector<std::vector<int>> voxel_labels;
+    std::vector<double> voxel_size;
+    double voxel_size_map = 1.0;
+    double max_range = 100.0;
+    double min_range = 5.0;
+    double label_max_range = 50.0;
+    double local_map_range = 100.0;
+    int basic_points_per_voxel = 20;
+    int critical_points_per_voxel = 20;
+    std::vector<int> basic_parts_labels;
+    double min_motion_th = 0.1;
+    double initial_threshold = 2.0;
+    double sem_th = 0.4;
+    bool deskew = false;
+    bool dynamic_vehicle_filter = false;
+    double dynamic_vehicle_filter_th = 0.5;
+    int dynamic_vehicle_voxid = 5;
+    std::vector<int> dynamic_remove_lankmark;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Preprocess, range branch — core/Preprocessing.cpp:173-187
+inline Cloud Preprocess(const Cloud &frame, double max_range, double min_range, double label_max_range) {
+    Cloud inliers;
+    for (const auto &point : frame) {
+        Point4 point_new = point;
+        const double nrm = norm(xyz(point));
+        if (nrm < max_range && nrm > min_range) {
+            if (nrm > label_max_range) point_new.l = 0.0;
+            inliers.emplace_back(point_new);
+        }
+    }
+    return inliers;
+}
+
+// VoxelDownsample — core/Preprocessing.cpp:44-84. The first `len` maps of grid_group are default-constructed
+// (bucket_count 0, unreserved, :50); the reserved copies appended at :52-56 are never used.
+inline Cloud VoxelDownsample(const Cloud &frame, const std::vector<std::vector<int>> &voxel_labels,
+                             const std::vector<double> &voxel_size, double vox_scale) {
+    const int len = (int)voxel_size.size();
+    std::vector<RobinTable<Point4>> grid_group(len);
+    for (const auto &point : frame) {
+        const int label = (int)point.l;
+        int group = -1;
+        for (int i = 0; i < len; i++) {
+            if (std::find(voxel_labels[i].begin(), voxel_labels[i].end(), label) != voxel_labels[i].end()) {
+                group = i;
+                break;
+            }
+        }
+        if (group == -1) continue;
+        const double s = voxel_size[group] * vox_scale;
+        const Voxel voxel{(int32_t)(point.x / s), (int32_t)(point.y / s), (int32_t)(point.z / s)};
+        if (grid_group[group].contains(voxel)) continue;
+        grid_group[group].insert(voxel, point);
+    }
+    Cloud out;
+    out.reserve(frame.size());
+    for (int i = 0; i < len; i++)
+        for (const auto &b : grid_group[i].buckets())
+            if (!b.empty()) out.emplace_back(b.value);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VoxelHashMap — core/VoxelHashMap.hpp:34-106, core/VoxelHashMap.cpp:48-184
+struct VoxelBlock {
+    std::vector<Point4> points;
+    int basic_part_ = 0;
+    int critical_part_ = 0;
+    std::vector<int> basic_parts_labels_;
+    // VoxelBlock::AddPoint — core/VoxelHashMap.hpp:45-70
+    void AddPoint(const Point4 &point) {
+        if (points.size() < (size_t)basic_part_) {
+            points.emplace_back(point);
+        } else {
+            const int label = (int)point.l;
+            if (label == 0) {
+            } else if (std::find(basic_parts_labels_.begin(), basic_parts_labels_.end(), label) != basic_parts_labels_.end()) {
+                for (auto &p : points)
+                    if ((int)p.l == 0) {
+                        p = point;
+                        break;
+                    }
+            } else {
+                if (points.size() < (size_t)(basic_part_ + critical_part_)) {
+                    points.emplace_back(point);
+                } else {
+                    for (auto &p : points)
+                        if ((int)p.l == 0) {
+                            p = point;
+                            break;
+                        }
+                }
+            }
+        }
+    }
+};
+
+struct Correspondences {
+    Cloud source, target;
+    std::vector<int64_t> query_index;  // oracle extra: which query each pair came from
+};
+
+struct VoxelHashMap {
+    double voxel_size_;
+    double max_distance_;
+    int basic_points_per_voxel_;
+    int critical_points_per_voxel_;
+    std::vector<int> basic_parts_labels_;
+    bool evict_faithful_ = true;
+    RobinTable<VoxelBlock> map_;
+
+    VoxelHashMap(double voxel_size, double max_distance, int basic, int critical, std::vector<int> basic_labels)
+        : voxel_size_(voxel_size), max_distance_(max_distance), basic_points_per_voxel_(basic),
+          critical_points_per_voxel_(critical), basic_parts_labels_(std::move(basic_labels)) {}
+
+    void Clear() { map_.clear(); }
+    bool Empty() const { return map_.empty(); }
+
+    // GetClosestNeighboor lambda — core/VoxelHashMap.cpp:51-96. Returns false when the 27-neighbourhood
+    // holds no point (reference: uninitialised read).
+    bool ClosestNeighbor(const Point4 &point, double th, Point4 &closest_neighbor) const {
+        const int kx = (int)(point.x / voxel_size_);
+        const int ky = (int)(point.y / voxel_size_);
+        const int kz = (int)(point.z / voxel_size_);
+        std::vector<Voxel> voxels;
+        voxels.reserve(27);
+        for (int i = kx - 1; i < kx + 1 + 1; ++i)
+            for (int j = ky - 1; j < ky + 1 + 1; ++j)
+                for (int k = kz - 1; k < kz + 1 + 1; ++k) voxels.push_back(Voxel{i, j, k});
+
+        Cloud neighboors;
+        neighboors.reserve(27 * (size_t)(basic_points_per_voxel_ + critical_points_per_voxel_));
+        for (const auto &voxel : voxels) {
+            const size_t ib = map_.find(voxel);
+            if (ib != map_.npos) {
+                const auto &pts = map_.value_at(ib).points;
+                for (const auto &pn : pts) neighboors.emplace_back(pn);
+            }
+        }
+        double closest_distance2 = std::numeric_limits<double>::max();
+        bool any = false;
+        for (const auto &nb : neighboors) {
+            const Vec3 d = xyz(nb) - xyz(point);
+            double distance = sqnorm(d);
+            if ((int)nb.l == (int)point.l || (int)(nb.l * point.l) == 0) distance = distance * th;
+            if (distance < closest_distance2) {
+                closest_neighbor = nb;
+                closest_distance2 = distance;
+                any = true;
+            }
+        }
+        return any;
+    }
+
+    // GetCorrespondences — core/VoxelHashMap.cpp:48-130. threads<=1: serial ("TBB off");
+    // threads>1: OpenMP static chunks, per-thread vectors concatenated in thread order.
+    Correspondences GetCorrespondences(const Cloud &points, double max_correspondance_distance, double th,
+                                       int threads = 1) const {
+        Correspondences out;
+        const int64_t n = (int64_t)points.size();
+        auto body = [&](int64_t lo, int64_t hi, Correspondences &res) {
+            res.source.reserve((size_t)(hi - lo));
+            res.target.reserve((size_t)(hi - lo));
+            for (int64_t i = lo; i < hi; ++i) {
+                const Point4 &point = points[(size_t)i];
+                Point4 cn;
+                if (!ClosestNeighbor(point, th, cn)) continue;
+                if (norm(xyz(cn) - xyz(point)) < max_correspondance_distance) {
+                    res.source.emplace_back(point);
+                    res.target.emplace_back(cn);
+                    res.query_index.push_back(i);
+                }
+            }
+        };
+#ifdef _OPENMP
+        if (threads > 1) {
+            std::vector<Correspondences> parts((size_t)threads);
+#pragma omp parallel num_threads(threads)
+            {
+                const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+                const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+                body(lo, hi, parts[(size_t)t]);
+            }
+            for (auto &p : parts) {
+                out.source.insert(out.source.end(), p.source.begin(), p.source.end());
+                out.target.insert(out.target.end(), p.target.begin(), p.target.end());
+                out.query_index.insert(out.query_index.end(), p.query_index.begin(), p.query_index.end());
+            }
+            return out;
+        }
+#endif
+        (void)threads;
+        body(0, n, out);
+        return out;
+    }
+
+    // Pointcloud — core/VoxelHashMap.cpp:132-142 (robin iteration order)
+    Cloud Pointcloud() const {
+        Cloud pts;
+        pts.reserve((size_t)(basic_points_per_voxel_ + critical_points_per_voxel_) * map_.size());
+        for (const auto &b : map_.buckets())
+            if (!b.empty())
+                for (const auto &p : b.value.points) pts.push_back(p);
+        return pts;
+    }
+
+    // AddPoints — core/VoxelHashMap.cpp:162-174 (strictly sequential)
+    void AddPoints(const Cloud &points) {
+        for (const auto &point : points) {
+            const Voxel voxel{(int32_t)(point.x / voxel_size_), (int32_t)(point.y / voxel_size_),
+                              (int32_t)(point.z / voxel_size_)};
+            const size_t ib = map_.find(voxel);
+            if (ib != map_.npos) {
+                map_.value_at(ib).AddPoint(point);
+            } else {
+                map_.insert(voxel, VoxelBlock{{point}, basic_points_per_voxel_, critical_points_per_voxel_, basic_parts_labels_});
+            }
+        }
+    }
+
+    // RemovePointsFarFromLocation — core/VoxelHashMap.cpp:176-184. Faithful mode reproduces the range-for +
+    // erase(key): after a backward-shift erase the iterator advances past the element shifted into the
+    // erased bucket, so that element is not tested this sweep.
+    void RemovePointsFarFromLocation(const Vec3 &origin) {
+        const double max_distance2 = max_distance_ * max_distance_;
+        auto &B = map_.buckets();
+        if (evict_faithful_) {
+            for (size_t ib = 0; ib < B.size(); ++ib) {
+                if (B[ib].empty()) continue;
+                const Vec3 pt = xyz(B[ib].value.points.front());
+                if (sqnorm(pt - origin) > max_distance2) map_.erase_at(ib);
+            }
+        } else {
+            std::vector<Voxel> far;
+            for (const auto &b : B)
+                if (!b.empty() && sqnorm(xyz(b.value.points.front()) - origin) > max_distance2) far.push_back(b.key);
+            for (const auto &k : far) map_.erase_at(map_.find(k));
+        }
+    }
+
+    void Update(const Cloud &points, const Vec3 &origin) {
+        AddPoints(points);
+        RemovePointsFarFromLocation(origin);
+    }
+    // Update(points, pose) — core/VoxelHashMap.cpp:149-160
+    void Update(const Cloud &points, const SE3 &pose) {
+        Cloud tr(points.size());
+        for (size_t i = 0; i < points.size(); ++i) {
+            const Vec3 t = se3_act(pose, xyz(points[i]));
+            tr[i] = {t.x, t.y, t.z, points[i].l};
+        }
+        Update(tr, pose.t);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Registration — core/Registration.cpp
+struct NormalEq {
+    double JTJ[6][6];
+    double JTr[6];
+    NormalEq() {
+        for (auto &r : JTJ)
+            for (auto &v : r) v = 0;
+        for (auto &v : JTr) v = 0;
+    }
+    void add(const NormalEq &o) {
+        for (int i = 0; i < 6; ++i) {
+            for (int j = 0; j < 6; ++j) JTJ[i][j] += o.JTJ[i][j];
+            JTr[i] += o.JTr[i];
+        }
+    }
+};
+
+// per-pair accumulation — core/Registration.cpp:62-70,79-85
+inline void accumulate_pair(NormalEq &ne, const Point4 &s, const Point4 &t, double th) {
+    const Vec3 src = xyz(s), tgt = xyz(t);
+    const Vec3 r = src - tgt;
+    double J[3][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}};
+    const Mat3 H = hat(src);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) J[i][3 + j] = -1.0 * H.m[i][j];
+    const double res2 = sqnorm(r);
+    const double w = (th * th) / ((th + res2) * (th + res2));
+    const double rv[3] = {r.x, r.y, r.z};
+    for (int i = 0; i < 6; ++i) {
+        for (int j = 0; j < 6; ++j) {
+            double acc = 0;
+            for (int k = 0; k < 3; ++k) acc += (J[k][i] * w) * J[k][j];
+            ne.JTJ[i][j] += acc;
+        }
+        double acc = 0;
+        for (int k = 0; k < 3; ++k) acc += (J[k][i] * w) * rv[k];
+        ne.JTr[i] += acc;
+    }
+}
+
+inline NormalEq BuildNormalEquations(const Cloud &source, const Cloud &target, double th, int threads = 1) {
+    NormalEq total;
+    const int64_t n = (int64_t)source.size();
+#ifdef _OPENMP
+    if (threads > 1) {
+        std::vector<NormalEq> parts((size_t)threads);
+#pragma omp parallel num_threads(threads)
+        {
+            const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+            const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+            for (int64_t i = lo; i < hi; ++i) accumulate_pair(parts[(size_t)t], source[(size_t)i], target[(size_t)i], th);
+        }
+        for (auto &p : parts) total.add(p);
+        return total;
+    }
+#endif
+    (void)threads;
+    for (int64_t i = 0; i < n; ++i) accumulate_pair(total, source[(size_t)i], target[(size_t)i], th);
+    return total;
+}
+
+// AlignClouds — core/Registration.cpp:59-94
+inline SE3 AlignClouds(const Cloud &source, const Cloud &target, double th, int threads = 1, NormalEq *ne_out = nullptr) {
+    const NormalEq ne = BuildNormalEquations(source, target, th, threads);
+    if (ne_out) *ne_out = ne;
+    double nb[6], x[6];
+    for (int i = 0; i < 6; ++i) nb[i] = -ne.JTr[i];
+    ldlt6_solve(ne.JTJ, nb, x);
+    return se3_exp(x);
+}
+
+constexpr int MAX_NUM_ITERATIONS_ = 500;             // core/Registration.cpp:96
+constexpr double ESTIMATION_THRESHOLD_ = 0.0001;     // core/Registration.cpp:97
+
+// TransformPoints — core/Registration.cpp:103-111
+inline void TransformPoints(const SE3 &T, Cloud &points) {
+    for (auto &p : points) {
+        const Vec3 t = se3_act(T, xyz(p));
+        p = {t.x, t.y, t.z, p.l};
+    }
+}
+
+// sage_icp::RegisterFrame — core/Registration.cpp:113-141. max_iters / est_th default to the reference's
+// constants; the kernel-level bench (BASELINE configs 2/4/5) fixes max_iters=10, est_th=0.
+inline SE3 RegisterFrameCore(const Cloud &frame, const VoxelHashMap &voxel_map, const SE3 &initial_guess,
+                             double max_correspondence_distance, double kernel, double sem_th, int threads = 1,
+                             int max_iters = MAX_NUM_ITERATIONS_, double est_th = ESTIMATION_THRESHOLD_,
+                             int *iters_out = nullptr) {
+    if (iters_out) *iters_out = 0;
+    if (voxel_map.Empty()) return initial_guess;
+    Cloud source = frame;
+    TransformPoints(initial_guess, source);
+    SE3 T_icp;
+    int j = 0;
+    while (j < max_iters) {
+        const auto corr = voxel_map.GetCorrespondences(source, max_correspondence_distance, sem_th, threads);
+        const SE3 estimation = AlignClouds(corr.source, corr.target, kernel, threads);
+        TransformPoints(estimation, source);
+        T_icp = se3_mul(estimation, T_icp);
+        ++j;  // j = iterations executed
+        double xi[6];
+        se3_log(estimation, xi);
+        double n2 = 0;
+        for (double v : xi) n2 += v * v;
+        if (std::sqrt(n2) < est_th) break;
+    }
+    if (iters_out) *iters_out = j;
+    return se3_mul(T_icp, initial_guess);
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdaptiveThreshold — core/Threshold.hpp:29-52, core/Threshold.cpp:29-50
+struct AdaptiveThreshold {
+    double initial_threshold_, min_motion_th_, max_range_;
+    double model_error_sse2_ = 0;
+    int num_samples_ = 0;
+    SE3 model_deviation_;
+    AdaptiveThreshold(double initial_threshold, double min_motion_th, double max_range)
+        : initial_threshold_(initial_threshold), min_motion_th_(min_motion_th), max_range_(max_range) {}
+    void UpdateModelDeviation(const SE3 &d) { model_deviation_ = d; }
+    double ComputeThreshold() {
+        const double theta = angle_of_rotation_matrix(quat_matrix(model_deviation_.q));
+        const double delta_rot = 2.0 * max_range_ * std::sin(theta / 2.0);
+        const double delta_trans = norm(model_deviation_.t);
+        const double model_error = delta_trans + delta_rot;
+        if (model_error > min_motion_th_) {
+            model_error_sse2_ += model_error * model_error;
+            num_samples_++;
+        }
+        if (num_samples_ < 1) return initial_threshold_;
+        return std::sqrt(model_error_sse2_ / num_samples_);
+    }
+};
+
+// DeSkewScan — core/Deskew.cpp:36-50
+inline Cloud DeSkewScan(const Cloud &frame, const std::vector<double> &timestamps, const SE3 &start_pose,
+                        const SE3 &finish_pose) {
+    double delta[6];
+    se3_log(se3_mul(se3_inverse(start_pose), finish_pose), delta);
+    Cloud out(frame.size());
+    for (size_t i = 0; i < frame.size(); ++i) {
+        double xi[6];
+        for (int k = 0; k < 6; ++k) xi[k] = (timestamps[i] - 0.5) * delta[k];
+        const Vec3 t = se3_act(se3_exp(xi), xyz(frame[i]));
+        out[i] = {t.x, t.y, t.z, frame[i].l};
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sageICP — pipeline/sageICP.hpp:67-109, pipeline/sageICP.cpp:36-129
+struct SageICP {
+    std::vector<SE3> poses_;
+    Config config_;
+    VoxelHashMap sem_map_;
+    AdaptiveThreshold adaptive_threshold_;
+    int threads_ = 1;
+    // oracle extras (diagnostics for parity tests)
+    Cloud last_frame_downsample_;
+    int last_iterations_ = 0;
+    double last_sigma_ = 0;
+
+    explicit SageICP(const Config &c)
+        : config_(c),
+          sem_map_(c.voxel_size_map, c.local_map_range, c.basic_points_per_voxel, c.critical_points_per_voxel, c.basic_parts_labels),
+          adaptive_threshold_(c.initial_threshold, c.min_motion_th, c.max_range) {}
+
+    // Voxelize — pipeline/sageICP.cpp:97-101; returns {source, frame_downsample}
+    std::tuple<Cloud, Cloud> Voxelize(const Cloud &frame) const {
+        Cloud frame_downsample = VoxelDownsample(frame, config_.voxel_labels, config_.voxel_size, 0.5);
+        Cloud source = VoxelDownsample(frame_downsample, config_.voxel_labels, config_.voxel_size, 1.5);
+        return {std::move(source), std::move(frame_downsample)};
+    }
+    bool HasMoved() {  // pipeline/sageICP.cpp:117-121
+        if (poses_.empty()) return false;
+        const double motion = norm(se3_mul(se3_inverse(poses_.front()), poses_.back()).t);
+        return motion > 5.0 * config_.min_motion_th;
+    }
+    double GetAdaptiveThreshold() {  // pipeline/sageICP.cpp:103-108
+        if (!HasMoved()) return config_.initial_threshold;
+        return adaptive_threshold_.ComputeThreshold();
+    }
+    SE3 GetPredictionModel() const {  // pipeline/sageICP.cpp:110-115
+        const size_t N = poses_.size();
+        if (N < 2) return SE3{};
+        return se3_mul(se3_inverse(poses_[N - 2]), poses_[N - 1]);
+    }
+    // RegisterFrame(frame) — pipeline/sageICP.cpp:54-95; returns {source, t_icp, t_all}
+    std::tuple<Cloud, double, double> RegisterFrame(const Cloud &frame) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        const Cloud cropped = Preprocess(frame, config_.max_range, config_.min_range, config_.label_max_range);
+        auto [source, frame_downsample] = Voxelize(cropped);
+        const double sigma = GetAdaptiveThreshold();
+        const SE3 prediction = GetPredictionModel();
+        const SE3 last_pose = !poses_.empty() ? poses_.back() : SE3{};
+        const SE3 initial_guess = se3_mul(last_pose, prediction);
+        auto t1 = std::chrono::high_resolution_clock::now();
+        const SE3 new_pose = RegisterFrameCore(source, sem_map_, initial_guess, 3.0 * sigma, sigma / 3.0, config_.sem_th,
+                                               threads_, MAX_NUM_ITERATIONS_, ESTIMATION_THRESHOLD_, &last_iterations_);
+        auto t2 = std::chrono::high_resolution_clock::now();
+        const SE3 model_deviation = se3_mul(se3_inverse(initial_guess), new_pose);
+        adaptive_threshold_.UpdateModelDeviation(model_deviation);
+        sem_map_.Update(frame_downsample, new_pose);
+        poses_.push_back(new_pose);
+        last_sigma_ = sigma;
+        last_frame_downsample_ = std::move(frame_downsample);
+        return {std::move(source), std::chrono::duration<double>(t2 - t1).count(), std::chrono::duration<double>(t2 - t0).count()};
+    }
+    // RegisterFrame(frame, timestamps) — pipeline/sageICP.cpp:36-52
+    std::tuple<Cloud, double, double> RegisterFrame(const Cloud &frame, const std::vector<double> &timestamps) {
+        if (!config_.deskew) return RegisterFrame(frame);
+        const size_t N = poses_.size();
+        if (N <= 2) return RegisterFrame(frame);
+        return RegisterFrame(DeSkewScan(frame, timestamps, poses_[N - 2], poses_[N - 1]));
+    }
+    // TransformToLastFrame — pipeline/sageICP.cpp:123-129
+    Cloud TransformToLastFrame(const SE3 &last_pose, const SE3 &current_pose, const Cloud &points) const {
+        Cloud out = points;
+        TransformPoints(se3_mul(se3_inverse(last_pose), current_pose), out);
+        return out;
+    }
+    Cloud LocalMap() const { return sem_map_.Pointcloud(); }
+    bool reinitialize() {  // pipeline/sageICP.hpp:94-99
+        poses_.clear();
+        adaptive_threshold_ = AdaptiveThreshold(config_.initial_threshold, config_.min_motion_th, config_.max_range);
+        sem_map_.Clear();
+        return true;
+    }
+};
+
+}  // namespace orc

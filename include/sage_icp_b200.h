@@ -1,0 +1,188 @@
+/*
+ * sage_icp_b200 — C ABI of the B200-native SAGE-ICP registration hot path.
+ *
+ * Plain C, POD-only: no Eigen / Sophus / torch types cross this boundary.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference repo, cpp/sage_icp/...).  The C++ adaptor with the
+ * reference's exact public surface lives in include/sage_icp/pipeline/sageICP.hpp and is a thin pimpl over
+ * these calls; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *   - points:  double[n][4] = x, y, z, label — bit-identical to std::vector<Eigen::Vector4d>::data().
+ *   - poses:   double[7]    = tx, ty, tz, qx, qy, qz, qw  (Sophus::SE3d: translation + unit quaternion).
+ *   - return:  0 / a count on success, negative SAGE_E* on failure; sage_last_error() gives the message.
+ *   - All compute runs on the handle's CUDA device.  There is NO CPU fallback: without a usable sm_100 device
+ *     sage_create()/sage_map_create() fail with SAGE_ENODEVICE.
+ *   - A handle is not thread-safe (the reference class is driven from one rclcpp executor thread,
+ *     ros/ros2/OdometryServer.cpp:356).
+ */
+#ifndef SAGE_ICP_B200_H_
+#define SAGE_ICP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAGE_OK 0
+#define SAGE_EINVAL -1    /* bad argument / config (e.g. no voxel groups: reference UB) */
+#define SAGE_ENODEVICE -2 /* no CUDA device / wrong architecture */
+#define SAGE_ECUDA -3     /* CUDA runtime error (message in sage_last_error) */
+#define SAGE_ERANGE -4    /* coordinate outside the packable voxel-key range */
+#define SAGE_ENCCL -5     /* NCCL unavailable or failed */
+#define SAGE_ECAPACITY -6 /* output buffer too small (needed count is returned through the out-param) */
+
+/* sage_icp::pipeline::sageConfig — pipeline/sageICP.hpp:39-65 (same fields; 2-D voxel_labels flattened). */
+typedef struct sage_config_pod {
+    int32_t n_groups;             /* voxel_labels.size() == voxel_size.size() */
+    const int32_t *group_offsets; /* n_groups+1 offsets into group_labels */
+    const int32_t *group_labels;
+    const double *voxel_size; /* n_groups */
+    double voxel_size_map, max_range, min_range, label_max_range, local_map_range;
+    int32_t basic_points_per_voxel, critical_points_per_voxel;
+    int32_t n_basic_parts_labels;
+    const int32_t *basic_parts_labels;
+    double min_motion_th, initial_threshold, sem_th;
+    int32_t deskew, dynamic_vehicle_filter;
+    double dynamic_vehicle_filter_th;
+    int32_t dynamic_vehicle_voxid;
+    int32_t n_dynamic_remove_lankmark;
+    const int32_t *dynamic_remove_lankmark;
+} sage_config_pod;
+
+typedef struct sage_pipeline sage_pipeline; /* sage_icp::pipeline::sageICP */
+typedef struct sage_map sage_map;           /* sage_icp::VoxelHashMap      */
+
+const char *sage_last_error(void);
+/* Number of visible CUDA devices with compute capability 10.x (0 => every create call fails loudly). */
+int sage_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Pipeline level — sage_icp::pipeline::sageICP (pipeline/sageICP.hpp:67-109)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* sageICP::sageICP(const sageConfig&) — pipeline/sageICP.hpp:73-76.  `device` = CUDA ordinal. */
+sage_pipeline *sage_create(const sage_config_pod *config, int device);
+void sage_destroy(sage_pipeline *h);
+/* sageICP::reinitialize() — pipeline/sageICP.hpp:94-99 */
+int sage_reset(sage_pipeline *h);
+
+/* sageICP::RegisterFrame(frame[, timestamps]) — pipeline/sageICP.cpp:36-52 and :54-95.
+ * xyzl: HOST pointer, n x 4 doubles.  timestamps: NULL or n doubles (used only when config.deskew).
+ * Outputs: new pose, t_icp / t_all in seconds (same meaning as the reference tuple: t_all excludes the map update).
+ * The returned `source` cloud of the reference tuple is fetched with sage_last_source(). */
+int sage_register_frame(sage_pipeline *h, const double *xyzl, size_t n, const double *timestamps, double pose_out[7],
+                        double *t_icp, double *t_all);
+/* std::get<0>(RegisterFrame(...)) — the double-downsampled query cloud, sensor frame, reference order. */
+int64_t sage_last_source(sage_pipeline *h, double *out, size_t cap_points);
+/* frame_downsample of the last frame (what Update() consumed) — diagnostic, pipeline/sageICP.cpp:68,92 */
+int64_t sage_last_frame_downsample(sage_pipeline *h, double *out, size_t cap_points);
+/* Iterations the last ICP ran and the sigma it used — diagnostics for parity tests. */
+int sage_last_iterations(sage_pipeline *h);
+double sage_last_sigma(sage_pipeline *h);
+
+/* sageICP::Voxelize — pipeline/sageICP.cpp:97-101.  Returns counts through n_source / n_downsample. */
+int sage_voxelize(sage_pipeline *h, const double *xyzl, size_t n, double *source_out, size_t *n_source,
+                  double *downsample_out, size_t *n_downsample);
+/* sageICP::GetAdaptiveThreshold (stateful, pipeline/sageICP.cpp:103-108), HasMoved (:117-121),
+ * GetPredictionModel (:110-115) */
+double sage_get_adaptive_threshold(sage_pipeline *h);
+int sage_has_moved(sage_pipeline *h);
+int sage_get_prediction_model(sage_pipeline *h, double pose_out[7]);
+/* sageICP::TransformToLastFrame — pipeline/sageICP.cpp:123-129 (points in/out may alias) */
+int sage_transform_to_last_frame(sage_pipeline *h, const double last_pose[7], const double current_pose[7],
+                                 const double *xyzl, size_t n, double *out);
+/* sageICP::poses() — pipeline/sageICP.hpp:93 */
+int64_t sage_num_poses(sage_pipeline *h);
+int sage_get_pose(sage_pipeline *h, size_t i, double pose_out[7]);
+/* sageICP::LocalMap() — pipeline/sageICP.hpp:92 -> VoxelHashMap::Pointcloud (core/VoxelHashMap.cpp:132-142).
+ * Same point set as the reference; order is device block order, not robin_map iteration order. */
+int64_t sage_local_map(sage_pipeline *h, double *out, size_t cap_points);
+/* The pipeline's map (borrowed; do not destroy). */
+sage_map *sage_pipeline_map(sage_pipeline *h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Core level — sage_icp::VoxelHashMap (core/VoxelHashMap.hpp) and the free functions of core/
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* VoxelHashMap::VoxelHashMap — core/VoxelHashMap.hpp:79-88 */
+sage_map *sage_map_create(double voxel_size, double max_distance, int basic_points_per_voxel,
+                          int critical_points_per_voxel, const int32_t *basic_parts_labels, int n_labels, int device);
+void sage_map_destroy(sage_map *m);
+int sage_map_clear(sage_map *m);                   /* VoxelHashMap::Clear  — core/VoxelHashMap.hpp:93 */
+int sage_map_empty(sage_map *m);                   /* VoxelHashMap::Empty  — core/VoxelHashMap.hpp:94 */
+int64_t sage_map_num_voxels(sage_map *m);
+int64_t sage_map_num_points(sage_map *m);
+/* VoxelHashMap::AddPoints — core/VoxelHashMap.cpp:162-174 (exact sequential AddPoint semantics per voxel) */
+int sage_map_add_points(sage_map *m, const double *xyzl, size_t n);
+/* VoxelHashMap::RemovePointsFarFromLocation — core/VoxelHashMap.cpp:176-184 ("clean" eviction: every voxel whose
+ * first point is farther than max_distance goes; see DESIGN.md on the reference's erase-while-iterating skip) */
+int sage_map_remove_far(sage_map *m, const double origin[3]);
+/* VoxelHashMap::Update(points, pose) — core/VoxelHashMap.cpp:149-160 */
+int sage_map_update(sage_map *m, const double *xyzl, size_t n, const double pose[7]);
+/* VoxelHashMap::Pointcloud — core/VoxelHashMap.cpp:132-142 */
+int64_t sage_map_pointcloud(sage_map *m, double *out, size_t cap_points);
+/* Bulk load of a pre-built map (voxel keys V x 3, per-voxel counts, points V x stride x 4 in stored order). */
+int sage_map_load(sage_map *m, const int32_t *keys, const int32_t *counts, const double *points, int stride,
+                  size_t n_voxels);
+/* Dump: keys V x 3, counts V, points V x stride x 4 (stride = basic+critical).  Returns V (call with NULLs to size). */
+int64_t sage_map_dump(sage_map *m, int32_t *keys, int32_t *counts, double *points, size_t cap_voxels);
+
+/* VoxelHashMap::GetCorrespondences — core/VoxelHashMap.cpp:48-130.
+ * target_out: n x 4 (valid where matched); matched_out: n flags; returns the number of pairs.  Pairs are reported
+ * per query index (the reference's TBB order is unspecified). */
+int64_t sage_map_get_correspondences(sage_map *m, const double *xyzl, size_t n, double max_correspondance_distance,
+                                     double th, double *target_out, uint8_t *matched_out);
+/* Exact neighbourhood statistics used for the algorithmic-bytes roofline figure. */
+int sage_map_nn_stats(sage_map *m, const double *xyzl, size_t n, uint64_t *occupied_voxels, uint64_t *candidates);
+
+/* sage_icp::RegisterFrame(frame, voxel_map, initial_guess, max_correspondence_distance, kernel, sem_th)
+ * — core/Registration.cpp:113-141.  max_iterations / estimation_threshold default to the reference's constants
+ * (500, 1e-4; core/Registration.cpp:96-97) when passed as <= 0 / < 0.  HOST buffers. */
+int sage_core_register_frame(sage_map *m, const double *frame_xyzl, size_t n, const double initial_guess[7],
+                             double max_correspondence_distance, double kernel, double sem_th, int max_iterations,
+                             double estimation_threshold, double pose_out[7], int *iterations_out);
+/* Same, DEVICE-resident frame (n x 4 doubles in HBM of the map's device); nothing crosses PCIe but the pose. */
+int sage_core_register_frame_device(sage_map *m, const void *frame_xyzl_dev, size_t n, const double initial_guess[7],
+                                    double max_correspondence_distance, double kernel, double sem_th,
+                                    int max_iterations, double estimation_threshold, double pose_out[7],
+                                    int *iterations_out);
+/* One AlignClouds evaluation (core/Registration.cpp:59-94) on the current correspondences of `frame` against the
+ * map: JTJ (36, row-major), JTr (6), and the number of pairs — for parity tests of the reduction. */
+int sage_core_normal_equations(sage_map *m, const double *frame_xyzl, size_t n, double max_correspondence_distance,
+                               double kernel, double sem_th, double JTJ_out[36], double JTr_out[6],
+                               int64_t *n_pairs_out);
+
+/* sage_icp::Preprocess, range branch — core/Preprocessing.cpp:173-187.  Returns the kept count. */
+int64_t sage_preprocess(sage_pipeline *h, const double *xyzl, size_t n, double *out, size_t cap_points);
+/* sage_icp::VoxelDownsample — core/Preprocessing.cpp:44-84 (reference output order). */
+int64_t sage_voxel_downsample(sage_pipeline *h, const double *xyzl, size_t n, double vox_scale, double *out,
+                              size_t cap_points);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Measurement and multi-GPU plumbing (no reference counterpart: the reference is single-process CPU)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* The CUDA stream (cudaStream_t) the map's kernels are launched on, for event timing by the caller. */
+void *sage_map_stream(sage_map *m);
+/* Per-kernel CUDA-event timing of the correspondence+normal-equation kernel.  enable=1 records an event pair around
+ * every launch; sage_map_profile_read() synchronises, returns launches and total milliseconds since the last read. */
+int sage_map_profile_enable(sage_map *m, int enable);
+int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms);
+/* Total kernel launches issued by this library in the calling process since load (bench.py's gpu_launches). */
+int64_t sage_launch_count(void);
+
+/* Query shard owned by `rank` out of `world` for n queries: contiguous [begin, end).  Pure host arithmetic. */
+int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end);
+/* NCCL plumbing for the sharded ICP: rank 0 calls sage_nccl_unique_id and ships the 128 bytes to its
+ * peers by any means; every rank then calls sage_map_comm_init.  After that sage_core_register_frame* treats its
+ * frame as this rank's shard and all-reduces the normal-equation sums (17 doubles) every iteration. */
+int sage_nccl_unique_id(uint8_t id_out[128]);
+int sage_map_comm_init(sage_map *m, int rank, int world, const uint8_t id[128]);
+int sage_map_comm_destroy(sage_map *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAGE_ICP_B200_H_ */

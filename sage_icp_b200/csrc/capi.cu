@@ -1,0 +1,329 @@
+// extern "C" surface declared in include/sage_icp_b200.h.  Exceptions never cross the boundary: they become
+// negative return codes + sage_last_error().
+#include <cstring>
+#include <string>
+
+#include "../../include/sage_icp_b200.h"
+#include "nccl_shim.cuh"
+#include "pipeline.cuh"
+
+using namespace sage;
+
+struct sage_map {
+    VoxelMapGPU *impl;
+    bool owned;
+};
+struct sage_pipeline {
+    Pipeline *impl;
+    sage_map map_handle;
+    std::vector<double> scratch;
+};
+
+static thread_local std::string g_err;
+
+template <class F>
+static long long guarded(F &&f) {
+    try {
+        return (long long)f();
+    } catch (const ArgError &e) {
+        g_err = e.what();
+        return SAGE_EINVAL;
+    } catch (const CudaError &e) {
+        g_err = e.what();
+        return SAGE_ECUDA;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        const bool nccl = std::strstr(e.what(), "nccl") || std::strstr(e.what(), "NCCL");
+        return nccl ? SAGE_ENCCL : SAGE_ECUDA;
+    }
+}
+
+static long long copy_out(const std::vector<double> &v, double *out, size_t cap_points) {
+    const size_t n = v.size() / 4;
+    if (!out) return (long long)n;
+    if (cap_points < n) {
+        g_err = "output buffer too small";
+        return SAGE_ECAPACITY;
+    }
+    if (n) std::memcpy(out, v.data(), v.size() * sizeof(double));
+    return (long long)n;
+}
+
+extern "C" {
+
+const char *sage_last_error(void) { return g_err.c_str(); }
+
+int sage_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+// ---- pipeline ---------------------------------------------------------------------------------
+sage_pipeline *sage_create(const sage_config_pod *config, int device) {
+    sage_pipeline *h = nullptr;
+    const long long rc = guarded([&] {
+        if (!config) throw ArgError("config is NULL");
+        auto *p = new Pipeline(*config, device);
+        h = new sage_pipeline{p, sage_map{&p->map(), false}, {}};
+        return 0;
+    });
+    return rc == 0 ? h : nullptr;
+}
+void sage_destroy(sage_pipeline *h) {
+    if (!h) return;
+    delete h->impl;
+    delete h;
+}
+int sage_reset(sage_pipeline *h) {
+    return (int)guarded([&] {
+        h->impl->reinitialize();
+        return 0;
+    });
+}
+int sage_register_frame(sage_pipeline *h, const double *xyzl, size_t n, const double *timestamps, double pose_out[7], double *t_icp,
+                        double *t_all) {
+    return (int)guarded([&] {
+        if (!h || (!xyzl && n)) throw ArgError("null argument");
+        Pose p;
+        double ti = 0, ta = 0;
+        h->impl->register_frame(xyzl, n, timestamps, p, ti, ta);
+        pose_to_wire(p, pose_out);
+        if (t_icp) *t_icp = ti;
+        if (t_all) *t_all = ta;
+        return 0;
+    });
+}
+int64_t sage_last_source(sage_pipeline *h, double *out, size_t cap) {
+    return guarded([&] {
+        if (!out) return (long long)h->impl->n_source();
+        h->impl->last_source(h->scratch);
+        return copy_out(h->scratch, out, cap);
+    });
+}
+int64_t sage_last_frame_downsample(sage_pipeline *h, double *out, size_t cap) {
+    return guarded([&] {
+        if (!out) return (long long)h->impl->n_downsample();
+        h->impl->last_downsample(h->scratch);
+        return copy_out(h->scratch, out, cap);
+    });
+}
+int sage_last_iterations(sage_pipeline *h) { return h->impl->last_iterations(); }
+double sage_last_sigma(sage_pipeline *h) { return h->impl->last_sigma(); }
+
+int sage_voxelize(sage_pipeline *h, const double *xyzl, size_t n, double *source_out, size_t *n_source, double *downsample_out,
+                  size_t *n_downsample) {
+    return (int)guarded([&] {
+        std::vector<double> s, d;
+        h->impl->voxelize_host(xyzl, n, s, d);
+        *n_source = s.size() / 4, *n_downsample = d.size() / 4;
+        if (source_out && !s.empty()) std::memcpy(source_out, s.data(), s.size() * sizeof(double));
+        if (downsample_out && !d.empty()) std::memcpy(downsample_out, d.data(), d.size() * sizeof(double));
+        return 0;
+    });
+}
+double sage_get_adaptive_threshold(sage_pipeline *h) { return h->impl->get_adaptive_threshold(); }
+int sage_has_moved(sage_pipeline *h) { return h->impl->has_moved() ? 1 : 0; }
+int sage_get_prediction_model(sage_pipeline *h, double pose_out[7]) {
+    pose_to_wire(h->impl->get_prediction_model(), pose_out);
+    return 0;
+}
+int sage_transform_to_last_frame(sage_pipeline *h, const double last_pose[7], const double current_pose[7], const double *xyzl, size_t n,
+                                 double *out) {
+    (void)h;
+    // TransformPoints(last_pose.inverse() * current_pose, points): a few thousand points for RViz; host arithmetic
+    const Pose T = pose_mul(pose_inverse(pose_from_wire(last_pose)), pose_from_wire(current_pose));
+    for (size_t i = 0; i < n; ++i) {
+        double x, y, z;
+        pose_act(T, xyzl[4 * i], xyzl[4 * i + 1], xyzl[4 * i + 2], x, y, z);
+        const double l = xyzl[4 * i + 3];
+        out[4 * i] = x, out[4 * i + 1] = y, out[4 * i + 2] = z, out[4 * i + 3] = l;
+    }
+    return 0;
+}
+int64_t sage_num_poses(sage_pipeline *h) { return (int64_t)h->impl->poses().size(); }
+int sage_get_pose(sage_pipeline *h, size_t i, double pose_out[7]) {
+    if (i >= h->impl->poses().size()) {
+        g_err = "pose index out of range";
+        return SAGE_EINVAL;
+    }
+    pose_to_wire(h->impl->poses()[i], pose_out);
+    return 0;
+}
+int64_t sage_local_map(sage_pipeline *h, double *out, size_t cap) {
+    return guarded([&] { return h->impl->map().pointcloud(out, cap); });
+}
+sage_map *sage_pipeline_map(sage_pipeline *h) { return &h->map_handle; }
+int64_t sage_preprocess(sage_pipeline *h, const double *xyzl, size_t n, double *out, size_t cap) {
+    return guarded([&] {
+        h->impl->preprocess_host(xyzl, n, h->scratch);
+        return copy_out(h->scratch, out, cap);
+    });
+}
+int64_t sage_voxel_downsample(sage_pipeline *h, const double *xyzl, size_t n, double vox_scale, double *out, size_t cap) {
+    return guarded([&] {
+        h->impl->downsample_host(xyzl, n, vox_scale, h->scratch);
+        return copy_out(h->scratch, out, cap);
+    });
+}
+
+// ---- map --------------------------------------------------------------------------------------
+sage_map *sage_map_create(double voxel_size, double max_distance, int basic, int critical, const int32_t *labels, int n_labels, int device) {
+    sage_map *m = nullptr;
+    const long long rc = guarded([&] {
+        m = new sage_map{new VoxelMapGPU(voxel_size, max_distance, basic, critical, labels, n_labels, device), true};
+        return 0;
+    });
+    return rc == 0 ? m : nullptr;
+}
+void sage_map_destroy(sage_map *m) {
+    if (!m || !m->owned) return;
+    delete m->impl;
+    delete m;
+}
+int sage_map_clear(sage_map *m) {
+    return (int)guarded([&] {
+        m->impl->clear();
+        return 0;
+    });
+}
+int sage_map_empty(sage_map *m) {
+    return (int)guarded([&] { return m->impl->empty() ? 1 : 0; });
+}
+int64_t sage_map_num_voxels(sage_map *m) {
+    return guarded([&] { return m->impl->num_voxels(); });
+}
+int64_t sage_map_num_points(sage_map *m) {
+    return guarded([&] { return m->impl->num_points(); });
+}
+int sage_map_add_points(sage_map *m, const double *xyzl, size_t n) {
+    return (int)guarded([&] {
+        m->impl->add_points_host(xyzl, n, nullptr);
+        return 0;
+    });
+}
+int sage_map_remove_far(sage_map *m, const double origin[3]) {
+    return (int)guarded([&] {
+        m->impl->remove_far(origin[0], origin[1], origin[2]);
+        return 0;
+    });
+}
+int sage_map_update(sage_map *m, const double *xyzl, size_t n, const double pose[7]) {
+    return (int)guarded([&] {
+        const Pose T = pose_from_wire(pose);
+        m->impl->add_points_host(xyzl, n, &T);
+        m->impl->remove_far(T.tx, T.ty, T.tz);
+        return 0;
+    });
+}
+int64_t sage_map_pointcloud(sage_map *m, double *out, size_t cap) {
+    return guarded([&] { return m->impl->pointcloud(out, cap); });
+}
+int sage_map_load(sage_map *m, const int32_t *keys, const int32_t *counts, const double *points, int stride, size_t n_voxels) {
+    return (int)guarded([&] {
+        m->impl->load(keys, counts, points, stride, n_voxels);
+        return 0;
+    });
+}
+int64_t sage_map_dump(sage_map *m, int32_t *keys, int32_t *counts, double *points, size_t cap_voxels) {
+    return guarded([&] { return m->impl->dump(keys, counts, points, cap_voxels); });
+}
+int64_t sage_map_get_correspondences(sage_map *m, const double *xyzl, size_t n, double max_dist, double th, double *target_out,
+                                     uint8_t *matched_out) {
+    return guarded([&] { return m->impl->get_correspondences(xyzl, n, max_dist, th, target_out, matched_out); });
+}
+int sage_map_nn_stats(sage_map *m, const double *xyzl, size_t n, uint64_t *occupied, uint64_t *candidates) {
+    return (int)guarded([&] {
+        unsigned long long o = 0, c = 0;
+        m->impl->nn_stats(xyzl, n, &o, &c);
+        *occupied = o, *candidates = c;
+        return 0;
+    });
+}
+int sage_core_register_frame(sage_map *m, const double *frame, size_t n, const double guess[7], double max_dist, double kernel,
+                             double sem_th, int max_iters, double est_th, double pose_out[7], int *iters_out) {
+    return (int)guarded([&] {
+        Pose out;
+        const int it = m->impl->register_frame_host(frame, n, pose_from_wire(guess), max_dist, kernel, sem_th, max_iters, est_th, out);
+        pose_to_wire(out, pose_out);
+        if (iters_out) *iters_out = it;
+        return 0;
+    });
+}
+int sage_core_register_frame_device(sage_map *m, const void *frame_dev, size_t n, const double guess[7], double max_dist, double kernel,
+                                    double sem_th, int max_iters, double est_th, double pose_out[7], int *iters_out) {
+    return (int)guarded([&] {
+        Pose out;
+        const int it = m->impl->register_frame_dev((const double4 *)frame_dev, n, pose_from_wire(guess), max_dist, kernel, sem_th,
+                                                   max_iters, est_th, out);
+        pose_to_wire(out, pose_out);
+        if (iters_out) *iters_out = it;
+        return 0;
+    });
+}
+int sage_core_normal_equations(sage_map *m, const double *frame, size_t n, double max_dist, double kernel, double sem_th,
+                               double JTJ[36], double JTr[6], int64_t *pairs) {
+    return (int)guarded([&] {
+        long long np = 0;
+        m->impl->normal_equations(frame, n, max_dist, kernel, sem_th, JTJ, JTr, &np);
+        if (pairs) *pairs = np;
+        return 0;
+    });
+}
+
+// ---- measurement / multi-GPU ------------------------------------------------------------------
+void *sage_map_stream(sage_map *m) { return (void *)m->impl->stream(); }
+int sage_map_profile_enable(sage_map *m, int enable) {
+    m->impl->profile_enable(enable != 0);
+    return 0;
+}
+int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms) {
+    return (int)guarded([&] {
+        long long l = 0;
+        double ms = 0;
+        m->impl->profile_read(&l, &ms);
+        if (launches) *launches = l;
+        if (total_ms) *total_ms = ms;
+        return 0;
+    });
+}
+int64_t sage_launch_count(void) { return g_launches.load(); }
+
+int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end) {
+    if (world < 1 || rank < 0 || rank >= world || !begin || !end) {
+        g_err = "bad shard arguments";
+        return SAGE_EINVAL;
+    }
+    // contiguous, balanced to within one query: rank r owns [n*r/world, n*(r+1)/world)
+    *begin = (size_t)(((unsigned __int128)n * (unsigned)rank) / (unsigned)world);
+    *end = (size_t)(((unsigned __int128)n * (unsigned)(rank + 1)) / (unsigned)world);
+    return 0;
+}
+int sage_nccl_unique_id(uint8_t id_out[128]) {
+    return (int)guarded([&] {
+        nccl_unique_id(id_out);
+        return 0;
+    });
+}
+int sage_map_comm_init(sage_map *m, int rank, int world, const uint8_t id[128]) {
+    return (int)guarded([&] {
+        m->impl->comm_init(rank, world, id);
+        return 0;
+    });
+}
+int sage_map_comm_destroy(sage_map *m) {
+    return (int)guarded([&] {
+        m->impl->comm_destroy();
+        return 0;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+// Range crop + per-label-group voxel downsample (sm_100a) with the reference's output order.
+//   Preprocess (range branch)   core/Preprocessing.cpp:173-187
+//   VoxelDownsample             core/Preprocessing.cpp:44-84
+//   DeSkewScan                  core/Deskew.cpp:36-50
+// Which point survives ("first point by input order per (group, voxel)") is a pure set property, computed with a
+// device hash grid and atomicMin on the point index.  The ORDER of the survivors is the iteration order of the
+// reference's unreserved tsl::robin_map per group; it decides the ICP query set and
+// the map insertion order, so it is reproduced exactly: the distinct keys' 20-bit hashes go to the host in
+// first-index order, robin_iteration_order() replays the table, and the permutation comes back for the gather.
+#include <algorithm>
+
+#include "frontend.cuh"
+
+namespace sage {
+
+constexpr int kFeThreads = 256;
+static inline unsigned fe_blocks(size_t n, int per_block = kFeThreads) { return (unsigned)((n + per_block - 1) / per_block); }
+
+// ---------------------------------------------------------------------------------------------
+// host: tsl::robin_map v1.0.1 iteration-order replay for distinct keys
+
+void robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out) {
+    // bucket arrays: dist (-1 = empty) and payload (input position)
+    std::vector<int16_t> dist, ndist;
+    std::vector<uint32_t> val, nval;
+    size_t B = 0, mask = 0, size = 0, load_threshold = 0;
+    bool grow_next = false;
+    constexpr int kDistLimit = 8192;
+
+    auto place = [&](std::vector<int16_t> &D, std::vector<uint32_t> &V, size_t msk, size_t ib, int d, uint32_t v, bool track) {
+        // robin-hood swap-and-carry from bucket ib with distance d
+        while (true) {
+            if (d > D[ib]) {
+                if (D[ib] < 0) {
+                    D[ib] = (int16_t)d, V[ib] = v;
+                    return;
+                }
+                if (track && d >= kDistLimit) grow_next = true;
+                const int od = D[ib];
+                const uint32_t ov = V[ib];
+                D[ib] = (int16_t)d, V[ib] = v;
+                d = od, v = ov;
+            }
+            ++d;
+            ib = (ib + 1) & msk;
+        }
+    };
+    auto rehash = [&](size_t count) {
+        ndist.assign(count, (int16_t)-1);
+        nval.assign(count, 0u);
+        const size_t nmask = count - 1;
+        for (size_t b = 0; b < B; ++b)
+            if (dist[b] >= 0) place(ndist, nval, nmask, hash20[val[b]] & nmask, 0, val[b], false);
+        dist.swap(ndist);
+        val.swap(nval);
+        B = count, mask = nmask;
+        load_threshold = (size_t)((float)count * 0.5f);
+    };
+
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t h = hash20[i];
+        size_t ib = 0;
+        int d = 0;
+        if (B) {
+            ib = h & mask;
+            while (d <= dist[ib]) ib = (ib + 1) & mask, ++d;
+        }
+        while (grow_next || d > kDistLimit || size >= load_threshold) {
+            rehash(B ? B * 2 : 2);
+            grow_next = false;
+            ib = h & mask, d = 0;
+            while (d <= dist[ib]) ib = (ib + 1) & mask, ++d;
+        }
+        place(dist, val, mask, ib, d, (uint32_t)i, true);
+        ++size;
+    }
+    size_t k = 0;
+    for (size_t b = 0; b < B; ++b)
+        if (dist[b] >= 0) order_out[k++] = val[b];
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+
+constexpr int kDsBits = 20;
+constexpr int kDsBias = 1 << (kDsBits - 1);
+
+__device__ __forceinline__ bool crop_point(const CropParams &c, double4 &p) {
+    if (!c.enabled) return true;
+    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(p.x, p.x), __dmul_rn(p.y, p.y)), __dmul_rn(p.z, p.z)));
+    if (!(nrm < c.max_range && nrm > c.min_range)) return false;
+    if (nrm > c.label_max_range) p.w = 0.0;
+    return true;
+}
+
+__device__ __forceinline__ uint32_t reference_voxel_hash(int x, int y, int z) {  // core/Preprocessing.cpp:35-40
+    return ((1u << 20) - 1u) & ((uint32_t)x * 73856093u ^ (uint32_t)y * 19349663u ^ (uint32_t)z * 83492791u);
+}
+
+__global__ void ds_insert_kernel(const double4 *in, uint32_t n, GroupTable g, CropParams crop, double scale,
+                                 unsigned long long *tkey, uint32_t *tfirst, uint32_t mask, uint32_t *slot_out, uint32_t *err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 p = in[i];
+    slot_out[i] = kNil;
+    if (!crop_point(crop, p)) return;
+    const int label = __double2int_rz(p.w);
+    int group = -1;
+    for (int k = 0; k < g.n_labels; ++k)
+        if (g.label[k] == label) {
+            group = g.group_of[k];
+            break;
+        }
+    if (group < 0) return;  // label in no group: dropped, core/Preprocessing.cpp:69
+    const double s = __dmul_rn(g.voxel_size[group], scale);
+    const int kx = trunc_div(p.x, s), ky = trunc_div(p.y, s), kz = trunc_div(p.z, s);
+    if (kx <= -kDsBias || kx >= kDsBias || ky <= -kDsBias || ky >= kDsBias || kz <= -kDsBias || kz >= kDsBias) {
+        atomicAdd(err, 1u);
+        return;
+    }
+    const unsigned long long key = (unsigned long long)(uint32_t)(kx + kDsBias) | ((unsigned long long)(uint32_t)(ky + kDsBias) << kDsBits) |
+                                   ((unsigned long long)(uint32_t)(kz + kDsBias) << (2 * kDsBits)) | ((unsigned long long)group << 60);
+    uint32_t sl = (uint32_t)mix64(key) & mask;
+    while (true) {
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(tkey + sl);
+        if (cur == key) break;
+        if (cur == kEmptyKey) {
+            const unsigned long long old = atomicCAS(tkey + sl, kEmptyKey, key);
+            if (old == kEmptyKey || old == key) break;
+        }
+        sl = (sl + 1) & mask;
+    }
+    atomicMin(tfirst + sl, i);  // first point by input order wins, core/Preprocessing.cpp:71-72
+    slot_out[i] = sl;
+}
+
+__global__ void ds_flag_kernel(const uint32_t *slot, const uint32_t *tfirst, uint32_t *flags, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slot[i];
+    flags[i] = (s != kNil && tfirst[s] == i) ? 1u : 0u;
+}
+
+__global__ void crop_flag_kernel(const double4 *in, uint32_t n, CropParams crop, uint32_t *flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 p = in[i];
+    flags[i] = crop_point(crop, p) ? 1u : 0u;
+}
+
+__global__ void crop_scatter_kernel(const double4 *in, uint32_t n, CropParams crop, const uint32_t *flags, const uint32_t *pos, double4 *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    double4 p = in[i];
+    crop_point(crop, p);
+    out[pos[i]] = p;
+}
+
+__global__ void ds_collect_kernel(const uint32_t *slot, const uint32_t *flags, const uint32_t *pos, const unsigned long long *tkey,
+                                  uint32_t *widx, uint32_t *whash, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const unsigned long long key = tkey[slot[i]];
+    const unsigned long long m = (1ull << kDsBits) - 1;
+    const int kx = (int)(key & m) - kDsBias, ky = (int)((key >> kDsBits) & m) - kDsBias, kz = (int)((key >> (2 * kDsBits)) & m) - kDsBias;
+    const uint32_t group = (uint32_t)(key >> 60);
+    const uint32_t j = pos[i];
+    widx[j] = i;
+    whash[j] = reference_voxel_hash(kx, ky, kz) | (group << 20);
+}
+
+__global__ void ds_gather_kernel(const double4 *in, const uint32_t *widx, const uint32_t *perm, CropParams crop, double4 *out, uint32_t m) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double4 p = in[widx[perm[j]]];
+    crop_point(crop, p);  // re-applies the far-label zeroing (core/Preprocessing.cpp:178)
+    out[j] = p;
+}
+
+// exclusive scan of 0/1 flags, 1024 elements per block
+__global__ void scan_block_kernel(const uint32_t *flags, uint32_t *pos, uint32_t *block_sums, uint32_t n) {
+    __shared__ uint32_t s[kFeThreads];
+    const uint32_t base = blockIdx.x * 1024u + threadIdx.x * 4u;
+    uint32_t v[4], e[4], run = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = (base + k < n) ? flags[base + k] : 0u;
+        e[k] = run;
+        run += v[k];
+    }
+    s[threadIdx.x] = run;
+    __syncthreads();
+    for (int o = 1; o < kFeThreads; o <<= 1) {
+        const uint32_t t = threadIdx.x >= (unsigned)o ? s[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s[threadIdx.x] += t;
+        __syncthreads();
+    }
+    const uint32_t excl = s[threadIdx.x] - run;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < n) pos[base + k] = excl + e[k];
+    if (threadIdx.x == kFeThreads - 1) block_sums[blockIdx.x] = s[threadIdx.x];
+}
+__global__ void scan_sums_kernel(uint32_t *block_sums, uint32_t nb, uint32_t *total) {
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+        const uint32_t v = block_sums[b];
+        block_sums[b] = run;
+        run += v;
+    }
+    total[0] = run;
+}
+__global__ void scan_add_kernel(uint32_t *pos, const uint32_t *block_sums, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] += block_sums[i / 1024u];
+}
+
+__global__ void deskew_kernel(const double4 *in, const double *ts, uint32_t n, double d0, double d1, double d2, double d3, double d4,
+                              double d5, double4 *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double s = ts[i] - 0.5;  // mid_pose_timestamp, core/Deskew.cpp:33
+    const double xi[6] = {s * d0, s * d1, s * d2, s * d3, s * d4, s * d5};
+    const Pose motion = pose_exp(xi);
+    const double4 p = in[i];
+    double x, y, z;
+    pose_act(motion, p.x, p.y, p.z, x, y, z);
+    out[i] = make_double4(x, y, z, p.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+
+FrontEnd::FrontEnd(const GroupTable &groups, int device, cudaStream_t stream) : groups_(groups), device_(device), stream_(stream) {
+    total_.ensure(2);
+    total_pin_.ensure(2);
+}
+
+void FrontEnd::scan_flags(size_t n) {
+    const unsigned nb = fe_blocks(n, 1024);
+    block_sums_.ensure(nb);
+    pos_.ensure(n);
+    SAGE_LAUNCH(scan_block_kernel, nb, kFeThreads, 0, stream_, flags_.p, pos_.p, block_sums_.p, (uint32_t)n);
+    SAGE_LAUNCH(scan_sums_kernel, 1, 1, 0, stream_, block_sums_.p, nb, total_.p);
+    SAGE_LAUNCH(scan_add_kernel, fe_blocks(n), kFeThreads, 0, stream_, pos_.p, block_sums_.p, (uint32_t)n);
+}
+
+size_t FrontEnd::preprocess(const double4 *in, size_t n, const CropParams &crop, double4 *out) {
+    SAGE_CUDA(cudaSetDevice(device_));
+    if (n == 0) return 0;
+    flags_.ensure(n);
+    SAGE_LAUNCH(crop_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, (uint32_t)n, crop, flags_.p);
+    scan_flags(n);
+    SAGE_LAUNCH(crop_scatter_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, (uint32_t)n, crop, flags_.p, pos_.p, out);
+    SAGE_CUDA(cudaMemcpyAsync(total_pin_.p, total_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    return total_pin_.p[0];
+}
+
+size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const CropParams &crop, double4 *out) {
+    SAGE_CUDA(cudaSetDevice(device_));
+    if (n == 0) return 0;
+    uint32_t cap = 1024;
+    while ((size_t)cap < 2 * n) cap *= 2;
+    if (cap > tcap_) {
+        tkey_.ensure(cap);
+        tfirst_.ensure(cap);
+        tcap_ = cap;
+    }
+    slot_.ensure(n);
+    flags_.ensure(n);
+    widx_.ensure(n);
+    whash_.ensure(n);
+    perm_.ensure(n);
+    whash_pin_.ensure(n);
+    perm_pin_.ensure(n);
+    SAGE_CUDA(cudaMemsetAsync(tkey_.p, 0xff, (size_t)cap * sizeof(unsigned long long), stream_));
+    SAGE_CUDA(cudaMemsetAsync(tfirst_.p, 0xff, (size_t)cap * sizeof(uint32_t), stream_));
+    SAGE_CUDA(cudaMemsetAsync(total_.p, 0, 2 * sizeof(uint32_t), stream_));
+    SAGE_LAUNCH(ds_insert_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, (uint32_t)n, groups_, crop, vox_scale, tkey_.p, tfirst_.p,
+                cap - 1, slot_.p, total_.p + 1);
+    SAGE_LAUNCH(ds_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, slot_.p, tfirst_.p, flags_.p, (uint32_t)n);
+    scan_flags(n);
+    SAGE_LAUNCH(ds_collect_kernel, fe_blocks(n), kFeThreads, 0, stream_, slot_.p, flags_.p, pos_.p, tkey_.p, widx_.p, whash_.p, (uint32_t)n);
+    SAGE_CUDA(cudaMemcpyAsync(total_pin_.p, total_.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    if (total_pin_.p[1]) throw ArgError("VoxelDownsample: point/voxel_size outside the +-2^19 voxel range");
+    const size_t m = total_pin_.p[0];
+    if (m == 0) return 0;
+    SAGE_CUDA(cudaMemcpyAsync(whash_pin_.p, whash_.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+
+    // per group: replay the robin_map on the distinct keys (first-index order) and emit groups in index order
+    // (core/Preprocessing.cpp:76-82)
+    size_t o = 0;
+    for (int g = 0; g < groups_.n_groups; ++g) {
+        seq_scratch_.clear();
+        order_scratch_.clear();
+        std::vector<uint32_t> &members = order_scratch_;
+        for (size_t j = 0; j < m; ++j)
+            if ((whash_pin_.p[j] >> 20) == (uint32_t)g) {
+                members.push_back((uint32_t)j);
+                seq_scratch_.push_back(whash_pin_.p[j] & 0xfffffu);
+            }
+        if (members.empty()) continue;
+        std::vector<uint32_t> ord(members.size());
+        robin_iteration_order(seq_scratch_.data(), seq_scratch_.size(), ord.data());
+        for (size_t k = 0; k < ord.size(); ++k) perm_pin_.p[o++] = members[ord[k]];
+    }
+    SAGE_CUDA(cudaMemcpyAsync(perm_.p, perm_pin_.p, m * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+    SAGE_LAUNCH(ds_gather_kernel, fe_blocks(m), kFeThreads, 0, stream_, in, widx_.p, perm_.p, crop, out, (uint32_t)m);
+    SAGE_CUDA(cudaStreamSynchronize(stream_));  // perm_pin_ is reused by the next call
+    return m;
+}
+
+void FrontEnd::deskew(const double4 *in, const double *ts, size_t n, const Pose &start, const Pose &finish, double4 *out) {
+    SAGE_CUDA(cudaSetDevice(device_));
+    if (n == 0) return;
+    double d[6];
+    pose_log(pose_mul(pose_inverse(start), finish), d);  // core/Deskew.cpp:40
+    SAGE_LAUNCH(deskew_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, ts, (uint32_t)n, d[0], d[1], d[2], d[3], d[4], d[5], out);
+}
+
+}  // namespace sage

@@ -1,0 +1,58 @@
+// Scan front end on the device: range crop + per-label-group voxel downsample with the reference's output order.
+// Mirrors sage_icp::Preprocess (range branch, core/Preprocessing.cpp:173-187), sage_icp::VoxelDownsample
+// (core/Preprocessing.cpp:44-84) and sage_icp::DeSkewScan (core/Deskew.cpp:36-50).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace sage {
+
+constexpr int kMaxGroups = 16;
+constexpr int kMaxGroupLabels = 64;
+
+struct GroupTable {  // passed to kernels by value
+    int n_groups;
+    int n_labels;
+    int label[kMaxGroupLabels];
+    int group_of[kMaxGroupLabels];  // parallel to label[], in first-match order
+    double voxel_size[kMaxGroups];
+};
+
+struct CropParams {
+    int enabled;
+    double max_range, min_range, label_max_range;
+};
+
+// Iteration order of a tsl::robin_map v1.0.1 that received `n` DISTINCT keys with the given 20-bit hashes in this
+// order.  order_out[j] = input position of the j-th element in iteration order.
+void robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out);
+
+class FrontEnd {
+public:
+    FrontEnd(const GroupTable &groups, int device, cudaStream_t stream);
+
+    // VoxelDownsample (optionally fused with the range crop) of a device-resident cloud.  Writes the result in the
+    // reference's order to `out` (device, capacity >= n) and returns the number of points kept.  Synchronises.
+    size_t downsample(const double4 *in, size_t n, double vox_scale, const CropParams &crop, double4 *out);
+    // Preprocess only (order-preserving compaction).  Returns kept count.  Synchronises.
+    size_t preprocess(const double4 *in, size_t n, const CropParams &crop, double4 *out);
+    // DeSkewScan on the device (in place allowed).
+    void deskew(const double4 *in, const double *timestamps_dev, size_t n, const Pose &start, const Pose &finish, double4 *out);
+
+private:
+    void scan_flags(size_t n);  // exclusive scan of flags_ -> pos_, total -> total_ (device)
+
+    GroupTable groups_;
+    int device_;
+    cudaStream_t stream_;
+    DevBuf<unsigned long long> tkey_;
+    DevBuf<uint32_t> tfirst_;
+    uint32_t tcap_ = 0;
+    DevBuf<uint32_t> slot_, flags_, pos_, block_sums_, widx_, whash_, perm_;
+    DevBuf<uint32_t> total_;
+    PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_;
+    std::vector<uint32_t> order_scratch_, seq_scratch_;
+};
+
+}  // namespace sage

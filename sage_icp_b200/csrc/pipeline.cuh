@@ -1,0 +1,56 @@
+// Host-side mirror of sage_icp::pipeline::sageICP (pipeline/sageICP.hpp:67-109) over the device kernels.
+#pragma once
+#include <vector>
+
+#include "../../include/sage_icp_b200.h"
+#include "frontend.cuh"
+#include "voxel_map.cuh"
+
+namespace sage {
+
+class Pipeline {
+public:
+    Pipeline(const sage_config_pod &config, int device);
+
+    void register_frame(const double *xyzl, size_t n, const double *timestamps, Pose &pose_out, double &t_icp, double &t_all);
+    void voxelize_host(const double *xyzl, size_t n, std::vector<double> &source, std::vector<double> &downsample);
+    double get_adaptive_threshold();
+    bool has_moved();
+    Pose get_prediction_model() const;
+    void reinitialize();
+    long long preprocess_host(const double *xyzl, size_t n, std::vector<double> &out);
+    long long downsample_host(const double *xyzl, size_t n, double scale, std::vector<double> &out);
+
+    const std::vector<Pose> &poses() const { return poses_; }
+    VoxelMapGPU &map() { return map_; }
+    void last_source(std::vector<double> &out) { fetch(src_.p, n_src_, out); }
+    void last_downsample(std::vector<double> &out) { fetch(ds_.p, n_ds_, out); }
+    size_t n_source() const { return n_src_; }
+    size_t n_downsample() const { return n_ds_; }
+    int last_iterations() const { return last_iters_; }
+    double last_sigma() const { return last_sigma_; }
+
+private:
+    void voxelize_dev(const double4 *frame, size_t n, const CropParams &cp);
+    void fetch(const double4 *dev, size_t n, std::vector<double> &out);
+    double compute_threshold();
+    void reset_threshold();
+    CropParams crop() const;
+
+    sage_config_pod cfg_;  // scalar fields only (array pointers nulled)
+    VoxelMapGPU map_;
+    FrontEnd fe_;
+    std::vector<Pose> poses_;
+    // AdaptiveThreshold state (core/Threshold.hpp:46-51)
+    double model_error_sse2_ = 0;
+    int num_samples_ = 0;
+    Pose model_deviation_ = pose_identity();
+
+    DevBuf<double4> ds_, src_, tmp_, deskewed_;
+    DevBuf<double> ts_;
+    size_t n_ds_ = 0, n_src_ = 0;
+    int last_iters_ = 0;
+    double last_sigma_ = 0;
+};
+
+}  // namespace sage

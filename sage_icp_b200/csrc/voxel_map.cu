@@ -1,0 +1,450 @@
+// Device-resident semantic voxel map: open-addressed hash (16-byte entries: key, block id, count) over a pool of
+// voxel blocks, each block = `stride` contiguous 32-byte point records (x, y, z, label as f64 — the very bytes of
+// the reference's Eigen::Vector4d).  Replaces sage_icp::VoxelHashMap's storage and update path:
+//   AddPoints                      core/VoxelHashMap.cpp:162-174  -> insert_keys / link / replay kernels
+//   VoxelBlock::AddPoint           core/VoxelHashMap.hpp:45-70    -> add_point_rule(), replayed per voxel in arrival order
+//   RemovePointsFarFromLocation    core/VoxelHashMap.cpp:176-184  -> evict kernel + table rebuild
+//   Update(points, pose)           core/VoxelHashMap.cpp:149-160  -> transform fused into insert_keys
+//   Pointcloud                     core/VoxelHashMap.cpp:132-142  -> pointcloud()
+// The reference's sequential insert is order dependent only *within* a voxel, so voxels are replayed in parallel,
+// each by one thread walking its arrivals in input order (exact).
+#include <algorithm>
+#include <cstring>
+
+#include "nccl_shim.cuh"
+#include "voxel_map.cuh"
+
+namespace sage {
+
+std::atomic<long long> g_launches{0};
+
+constexpr int kThreads = 256;
+static inline unsigned blocks_for(size_t n, int threads = kThreads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+
+__global__ void tbl_clear_kernel(TblEntry *tbl, uint32_t cap, const MapCtrl *ctrl, int only_if_evicted) {
+    if (only_if_evicted && ctrl->evicted == 0) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) tbl[i] = TblEntry{kEmptyKey, kNil, 0};
+}
+
+__device__ __forceinline__ uint32_t tbl_insert_slot(TblEntry *tbl, uint32_t mask, unsigned long long key, bool &won) {
+    uint32_t i = (uint32_t)mix64(key) & mask;
+    won = false;
+    while (true) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&tbl[i].key);
+        if (cur == key) return i;
+        if (cur == kEmptyKey) {
+            const unsigned long long old = atomicCAS(&tbl[i].key, kEmptyKey, key);
+            if (old == kEmptyKey) {
+                won = true;
+                return i;
+            }
+            if (old == key) return i;
+        }
+        i = (i + 1) & mask;
+    }
+}
+
+// re-insert every live block (after eviction or growth)
+__global__ void tbl_reinsert_kernel(MapView m, int only_if_evicted) {
+    if (only_if_evicted && m.ctrl->evicted == 0) return;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m.ctrl->n_hi) return;
+    const unsigned long long key = m.blk_key[b];
+    if (key == kEmptyKey) return;
+    bool won;
+    const uint32_t s = tbl_insert_slot(m.tbl, m.mask, key, won);
+    m.tbl[s].block = b;
+    m.tbl[s].count = (uint32_t)m.blk_cnt[b];
+    m.blk_slot[b] = s;
+}
+
+__global__ void ctrl_finish_kernel(MapCtrl *ctrl) {
+    ctrl->evicted = 0;
+    if (ctrl->n_free < 0) ctrl->n_free = 0;
+}
+
+// phase 1 of AddPoints: (optionally) transform, compute the voxel key, find-or-create the voxel.
+__global__ void map_insert_keys_kernel(MapView m, const double4 *in, double4 *pts, uint32_t *slot_out, uint32_t n, int has_pose,
+                                       Pose pose) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 p = in[i];
+    if (has_pose) {  // pose * point, core/VoxelHashMap.cpp:151-157
+        double x, y, z;
+        pose_act(pose, p.x, p.y, p.z, x, y, z);
+        p.x = x, p.y = y, p.z = z;
+    }
+    pts[i] = p;
+    // Voxel((point / voxel_size_).cast<int>()), core/VoxelHashMap.cpp:165
+    const int kx = trunc_div(p.x, m.voxel_size), ky = trunc_div(p.y, m.voxel_size), kz = trunc_div(p.z, m.voxel_size);
+    if (!key_in_range(kx, ky, kz)) {
+        slot_out[i] = kNil;
+        atomicAdd(&m.ctrl->range_err, 1u);
+        return;
+    }
+    const unsigned long long key = pack_key(kx, ky, kz);
+    bool won;
+    const uint32_t s = tbl_insert_slot(m.tbl, m.mask, key, won);
+    if (won) {
+        const int f = atomicSub(&m.ctrl->n_free, 1);
+        uint32_t b;
+        if (f > 0)
+            b = m.free_list[f - 1];
+        else
+            b = atomicAdd(&m.ctrl->n_hi, 1u);
+        if (b >= m.blk_cap) {
+            atomicExch(&m.ctrl->overflow, 1u);
+            b = m.blk_cap - 1;
+        }
+        m.blk_key[b] = key;
+        m.blk_cnt[b] = 0;
+        m.blk_head[b] = kNil;
+        m.blk_slot[b] = s;
+        m.tbl[s].count = 0;
+        m.tbl[s].block = b;
+        atomicAdd(&m.ctrl->n_live, 1u);
+    }
+    slot_out[i] = s;
+}
+
+// phase 2: push every point on its voxel's arrival list
+__global__ void map_link_kernel(MapView m, const uint32_t *slot, uint32_t *next, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && m.ctrl->n_free < 0) m.ctrl->n_free = 0;
+    if (i >= n) return;
+    const uint32_t s = slot[i];
+    if (s == kNil) {
+        next[i] = kNil - 1;  // not on any list
+        return;
+    }
+    const uint32_t b = m.tbl[s].block;
+    next[i] = atomicExch(&m.blk_head[b], i);
+}
+
+// VoxelBlock::AddPoint — core/VoxelHashMap.hpp:45-70
+__device__ __forceinline__ void add_point_rule(const MapView &m, double4 *vox, int &cnt, const double4 &p) {
+    if (cnt < m.basic || cnt == 0) {  // cnt == 0: a new voxel is created holding its first point whatever the label
+        vox[cnt++] = p;
+        return;
+    }
+    const int label = __double2int_rz(p.w);
+    if (label == 0) return;
+    bool is_basic = false;
+    for (int k = 0; k < m.n_basic_labels; ++k) is_basic |= (m.basic_labels[k] == label);
+    if (!is_basic && cnt < m.basic + m.critical) {
+        vox[cnt++] = p;
+        return;
+    }
+    for (int k = 0; k < cnt; ++k)
+        if (__double2int_rz(vox[k].w) == 0) {
+            vox[k] = p;
+            return;
+        }
+}
+
+// phase 3: the thread whose point was pushed first (next == nil) replays that voxel's arrivals in input order
+__global__ void map_replay_kernel(MapView m, const double4 *pts, const uint32_t *slot, uint32_t *next, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || next[i] != kNil) return;
+    const uint32_t s = slot[i];
+    const uint32_t b = m.tbl[s].block;
+    const uint32_t head = m.blk_head[b];
+    double4 *vox = m.blk_pts + (size_t)b * m.stride;
+    int cnt = m.blk_cnt[b];
+    long long last = -1;
+    while (true) {
+        uint32_t best = kNil;
+        for (uint32_t j = head; j != kNil; j = next[j])
+            if ((long long)j > last && j < best) best = j;
+        if (best == kNil) break;
+        add_point_rule(m, vox, cnt, pts[best]);
+        last = best;
+    }
+    m.blk_cnt[b] = cnt;
+    m.tbl[s].count = (uint32_t)cnt;
+    m.blk_head[b] = kNil;
+}
+
+// RemovePointsFarFromLocation — core/VoxelHashMap.cpp:176-184, "clean" semantics (every far voxel goes)
+__global__ void map_evict_kernel(MapView m, double ox, double oy, double oz, double max_d2) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m.ctrl->n_hi) return;
+    if (m.blk_key[b] == kEmptyKey) return;
+    const double4 f = m.blk_pts[(size_t)b * m.stride];  // voxel_block.points.front()
+    const double dx = __dsub_rn(f.x, ox), dy = __dsub_rn(f.y, oy), dz = __dsub_rn(f.z, oz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (d2 > max_d2) {
+        m.blk_key[b] = kEmptyKey;
+        m.blk_cnt[b] = 0;
+        const int idx = atomicAdd(&m.ctrl->n_free, 1);
+        m.free_list[idx] = b;
+        atomicSub(&m.ctrl->n_live, 1u);
+        atomicAdd(&m.ctrl->evicted, 1u);
+    }
+}
+
+__global__ void map_count_points_kernel(MapView m) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (b < m.ctrl->n_hi && m.blk_key[b] != kEmptyKey) c = (unsigned long long)m.blk_cnt[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&m.ctrl->n_points, c);
+}
+
+__global__ void ctrl_set_kernel(MapCtrl *ctrl, uint32_t n_hi, uint32_t n_live) {
+    ctrl->n_hi = n_hi, ctrl->n_free = 0, ctrl->n_live = n_live, ctrl->evicted = 0, ctrl->overflow = 0, ctrl->range_err = 0;
+    ctrl->n_points = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host class
+
+VoxelMapGPU::VoxelMapGPU(double voxel_size, double max_distance, int basic, int critical, const int32_t *labels, int n_labels,
+                         int device)
+    : voxel_size_(voxel_size), max_distance_(max_distance), basic_(basic), critical_(critical), stride_(basic + critical),
+      basic_labels_(labels, labels + n_labels), device_(device) {
+    if (!(voxel_size > 0) || basic < 0 || critical < 0 || basic + critical < 1) throw ArgError("bad voxel map parameters");
+    if (n_labels > 32) throw ArgError("at most 32 basic_parts_labels supported");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        throw CudaError("no usable CUDA device " + std::to_string(device) + " (sage_icp_b200 has no CPU fallback)");
+    cudaDeviceProp prop;
+    SAGE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw CudaError(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", need sm_100 (B200)");
+    sm_count_ = prop.multiProcessorCount;
+    set_device();
+    SAGE_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    ctrl_.ensure(1);
+    ctrl_pin_.ensure(1);
+    icp_.ensure(1);
+    icp_pin_.ensure(1);
+    clear();
+}
+
+VoxelMapGPU::~VoxelMapGPU() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    comm_destroy();
+    for (auto &e : prof_events_) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+MapView VoxelMapGPU::view() {
+    MapView v;
+    v.tbl = tbl_.p, v.mask = tbl_cap_ - 1;
+    v.blk_key = blk_key_.p, v.blk_cnt = blk_cnt_.p, v.blk_head = blk_head_.p, v.blk_slot = blk_slot_.p, v.blk_pts = blk_pts_.p;
+    v.free_list = free_list_.p, v.ctrl = ctrl_.p;
+    v.stride = stride_, v.basic = basic_, v.critical = critical_;
+    v.n_basic_labels = (int)basic_labels_.size();
+    for (int i = 0; i < 32; ++i) v.basic_labels[i] = i < (int)basic_labels_.size() ? basic_labels_[i] : 0;
+    v.voxel_size = voxel_size_;
+    v.blk_cap = blk_cap_;
+    return v;
+}
+
+void VoxelMapGPU::clear() {
+    set_device();
+    if (tbl_cap_ == 0) {
+        tbl_cap_ = 1u << 16;
+        tbl_.ensure(tbl_cap_);
+    }
+    SAGE_LAUNCH(tbl_clear_kernel, blocks_for(tbl_cap_), kThreads, 0, stream_, tbl_.p, tbl_cap_, ctrl_.p, 0);
+    SAGE_LAUNCH(ctrl_set_kernel, 1, 1, 0, stream_, ctrl_.p, 0u, 0u);
+    hi_bound_ = live_bound_ = 0;
+    host_stats_ = MapCtrl{};
+}
+
+void VoxelMapGPU::sync_stats() {
+    set_device();
+    SAGE_CUDA(cudaMemcpyAsync(ctrl_pin_.p, ctrl_.p, sizeof(MapCtrl), cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    host_stats_ = *ctrl_pin_.p;
+    hi_bound_ = host_stats_.n_hi;
+    live_bound_ = host_stats_.n_live;
+    if (host_stats_.overflow) throw CudaError("voxel map pool overflow (internal capacity bound violated)");
+}
+
+bool VoxelMapGPU::empty() {
+    if (live_bound_ == 0) return true;
+    sync_stats();
+    return host_stats_.n_live == 0;
+}
+
+long long VoxelMapGPU::num_voxels() {
+    sync_stats();
+    return host_stats_.n_live;
+}
+
+long long VoxelMapGPU::num_points() {
+    set_device();
+    sync_stats();
+    if (host_stats_.n_hi == 0) return 0;
+    SAGE_CUDA(cudaMemsetAsync(&ctrl_.p->n_points, 0, sizeof(unsigned long long), stream_));
+    SAGE_LAUNCH(map_count_points_kernel, blocks_for(host_stats_.n_hi), kThreads, 0, stream_, view());
+    sync_stats();
+    return (long long)host_stats_.n_points;
+}
+
+void VoxelMapGPU::rebuild_table(uint32_t new_cap) {
+    if (new_cap != tbl_cap_) {
+        tbl_.ensure(new_cap);
+        tbl_cap_ = new_cap;
+    }
+    SAGE_LAUNCH(tbl_clear_kernel, blocks_for(tbl_cap_), kThreads, 0, stream_, tbl_.p, tbl_cap_, ctrl_.p, 0);
+    if (hi_bound_ > 0) SAGE_LAUNCH(tbl_reinsert_kernel, blocks_for(hi_bound_), kThreads, 0, stream_, view(), 0);
+}
+
+void VoxelMapGPU::reserve(size_t extra) {
+    set_device();
+    const bool need_blocks = hi_bound_ + extra > blk_cap_;
+    const bool need_tbl = 2 * (live_bound_ + extra) > tbl_cap_;
+    if (need_blocks || need_tbl) sync_stats();  // tighten the bounds before paying for growth
+    if (hi_bound_ + extra > blk_cap_) {
+        size_t want = std::max<size_t>(hi_bound_ + extra, (size_t)blk_cap_ * 2);
+        want = std::max<size_t>(want, 4096);
+        if (want > 0x7fffffffull / (size_t)stride_) throw ArgError("voxel map too large");
+        blk_key_.ensure(want, stream_, true);
+        blk_cnt_.ensure(want, stream_, true);
+        blk_head_.ensure(want, stream_, true);
+        blk_slot_.ensure(want, stream_, true);
+        free_list_.ensure(want, stream_, true);
+        blk_pts_.ensure(want * (size_t)stride_, stream_, true);
+        blk_cap_ = (uint32_t)std::min<size_t>({blk_key_.cap, blk_cnt_.cap, blk_head_.cap, blk_slot_.cap, free_list_.cap,
+                                                blk_pts_.cap / (size_t)stride_});
+    }
+    if (2 * (live_bound_ + extra) > tbl_cap_) {
+        uint32_t cap = tbl_cap_;
+        while ((size_t)cap < 2 * (live_bound_ + extra)) cap *= 2;
+        rebuild_table(cap);
+    }
+}
+
+void VoxelMapGPU::add_points_dev(const double4 *pts, size_t n, const Pose *pose) {
+    set_device();
+    const size_t kChunk = 1u << 22;  // bounds scratch; chunks are applied in order so semantics are unchanged
+    for (size_t off = 0; off < n; off += kChunk) {
+        const uint32_t m = (uint32_t)std::min(kChunk, n - off);
+        reserve(m);
+        upd_pts_.ensure(m);
+        upd_slot_.ensure(m);
+        upd_next_.ensure(m);
+        MapView v = view();
+        SAGE_LAUNCH(map_insert_keys_kernel, blocks_for(m), kThreads, 0, stream_, v, pts + off, upd_pts_.p, upd_slot_.p, m,
+                    pose ? 1 : 0, pose ? *pose : pose_identity());
+        SAGE_LAUNCH(map_link_kernel, blocks_for(m), kThreads, 0, stream_, v, upd_slot_.p, upd_next_.p, m);
+        SAGE_LAUNCH(map_replay_kernel, blocks_for(m), kThreads, 0, stream_, v, upd_pts_.p, upd_slot_.p, upd_next_.p, m);
+        hi_bound_ += m;
+        live_bound_ += m;
+    }
+}
+
+void VoxelMapGPU::add_points_host(const double *xyzl, size_t n, const Pose *pose) {
+    const size_t kChunk = 1u << 22;
+    for (size_t off = 0; off < n; off += kChunk) {
+        const size_t m = std::min(kChunk, n - off);
+        double4 *d = stage_points(xyzl + 4 * off, m);
+        add_points_dev(d, m, pose);
+        SAGE_CUDA(cudaStreamSynchronize(stream_));  // staging buffer is reused by the next chunk
+    }
+}
+
+void VoxelMapGPU::remove_far(double ox, double oy, double oz) {
+    set_device();
+    if (hi_bound_ == 0) return;
+    MapView v = view();
+    SAGE_LAUNCH(map_evict_kernel, blocks_for(hi_bound_), kThreads, 0, stream_, v, ox, oy, oz, max_distance_ * max_distance_);
+    SAGE_LAUNCH(tbl_clear_kernel, blocks_for(tbl_cap_), kThreads, 0, stream_, tbl_.p, tbl_cap_, ctrl_.p, 1);
+    SAGE_LAUNCH(tbl_reinsert_kernel, blocks_for(hi_bound_), kThreads, 0, stream_, v, 1);
+    SAGE_LAUNCH(ctrl_finish_kernel, 1, 1, 0, stream_, ctrl_.p);
+}
+
+long long VoxelMapGPU::dump(int32_t *keys, int32_t *counts, double *points, size_t cap_voxels) {
+    set_device();
+    sync_stats();
+    const size_t hi = host_stats_.n_hi, live = host_stats_.n_live;
+    if (!keys || cap_voxels < live) return (long long)live;
+    std::vector<unsigned long long> k(hi);
+    std::vector<int32_t> c(hi);
+    std::vector<double> p(hi * (size_t)stride_ * 4);
+    if (hi) {
+        SAGE_CUDA(cudaMemcpyAsync(k.data(), blk_key_.p, hi * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+        SAGE_CUDA(cudaMemcpyAsync(c.data(), blk_cnt_.p, hi * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        SAGE_CUDA(cudaMemcpyAsync(p.data(), blk_pts_.p, hi * (size_t)stride_ * sizeof(double4), cudaMemcpyDeviceToHost, stream_));
+        SAGE_CUDA(cudaStreamSynchronize(stream_));
+    }
+    size_t v = 0;
+    for (size_t b = 0; b < hi; ++b) {
+        if (k[b] == kEmptyKey) continue;
+        int x, y, z;
+        unpack_key(k[b], x, y, z);
+        keys[3 * v] = x, keys[3 * v + 1] = y, keys[3 * v + 2] = z;
+        counts[v] = c[b];
+        std::memset(points + v * (size_t)stride_ * 4, 0, sizeof(double) * 4 * (size_t)stride_);
+        std::memcpy(points + v * (size_t)stride_ * 4, p.data() + b * (size_t)stride_ * 4, sizeof(double) * 4 * (size_t)c[b]);
+        ++v;
+    }
+    return (long long)v;
+}
+
+long long VoxelMapGPU::pointcloud(double *out, size_t cap_points) {
+    const long long total = num_points();
+    if (!out || cap_points < (size_t)total) return total;
+    const size_t live = host_stats_.n_live;
+    std::vector<int32_t> keys(3 * live + 3), counts(live + 1);
+    std::vector<double> pts((live + 1) * (size_t)stride_ * 4);
+    const long long v = dump(keys.data(), counts.data(), pts.data(), live);
+    size_t o = 0;
+    for (long long b = 0; b < v; ++b) {
+        std::memcpy(out + 4 * o, pts.data() + (size_t)b * stride_ * 4, sizeof(double) * 4 * (size_t)counts[b]);
+        o += (size_t)counts[b];
+    }
+    return (long long)o;
+}
+
+void VoxelMapGPU::load(const int32_t *keys, const int32_t *counts, const double *points, int stride, size_t n_voxels) {
+    set_device();
+    clear();
+    if (n_voxels == 0) return;
+    reserve(n_voxels);
+    std::vector<unsigned long long> k(n_voxels);
+    std::vector<int32_t> c(n_voxels);
+    std::vector<double> p(n_voxels * (size_t)stride_ * 4, 0.0);
+    for (size_t v = 0; v < n_voxels; ++v) {
+        if (!key_in_range(keys[3 * v], keys[3 * v + 1], keys[3 * v + 2])) throw ArgError("voxel key outside packable range");
+        if (counts[v] < 0 || counts[v] > stride_ || counts[v] > stride) throw ArgError("voxel count exceeds basic+critical");
+        k[v] = pack_key(keys[3 * v], keys[3 * v + 1], keys[3 * v + 2]);
+        c[v] = counts[v];
+        std::memcpy(p.data() + v * (size_t)stride_ * 4, points + v * (size_t)stride * 4, sizeof(double) * 4 * (size_t)counts[v]);
+    }
+    SAGE_CUDA(cudaMemcpyAsync(blk_key_.p, k.data(), n_voxels * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream_));
+    SAGE_CUDA(cudaMemcpyAsync(blk_cnt_.p, c.data(), n_voxels * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    SAGE_CUDA(cudaMemcpyAsync(blk_pts_.p, p.data(), p.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    SAGE_CUDA(cudaMemsetAsync(blk_head_.p, 0xff, n_voxels * sizeof(uint32_t), stream_));
+    SAGE_LAUNCH(ctrl_set_kernel, 1, 1, 0, stream_, ctrl_.p, (uint32_t)n_voxels, (uint32_t)n_voxels);
+    hi_bound_ = live_bound_ = n_voxels;
+    rebuild_table(tbl_cap_);
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void VoxelMapGPU::comm_init(int rank, int world, const uint8_t id[128]) {
+    set_device();
+    comm_destroy();
+    comm_ = nccl_comm_create(rank, world, id);
+}
+
+void VoxelMapGPU::comm_destroy() {
+    if (comm_) {
+        nccl_comm_destroy(comm_);
+        comm_ = nullptr;
+    }
+}
+
+}  // namespace sage

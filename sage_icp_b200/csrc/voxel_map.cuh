@@ -1,0 +1,128 @@
+// Device-resident semantic voxel map + registration driver (host class).
+// Mirrors sage_icp::VoxelHashMap (core/VoxelHashMap.hpp:34-106) and sage_icp::RegisterFrame
+// (core/Registration.cpp:113-141).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace sage {
+
+struct NcclComm;  // nccl_shim.cu
+
+// Raw device view handed to kernels.
+struct MapView {
+    TblEntry *tbl;
+    uint32_t mask;  // capacity - 1
+    unsigned long long *blk_key;
+    int32_t *blk_cnt;
+    uint32_t *blk_head;  // per-block arrival list head (kNil between updates)
+    uint32_t *blk_slot;  // table slot of the block
+    double4 *blk_pts;    // [block][stride] x, y, z, label — bit-identical to Eigen::Vector4d
+    uint32_t *free_list;
+    MapCtrl *ctrl;
+    int stride;  // basic + critical
+    int basic, critical;
+    int n_basic_labels;
+    int basic_labels[32];
+    double voxel_size;
+    uint32_t blk_cap;
+};
+
+class VoxelMapGPU {
+public:
+    VoxelMapGPU(double voxel_size, double max_distance, int basic, int critical, const int32_t *labels, int n_labels, int device);
+    ~VoxelMapGPU();
+
+    void clear();
+    bool empty();
+    long long num_voxels();
+    long long num_points();
+
+    // points already on the device, n x double4; pose == nullptr -> points are already in the map frame
+    void add_points_dev(const double4 *pts, size_t n, const Pose *pose);
+    void add_points_host(const double *xyzl, size_t n, const Pose *pose);
+    void remove_far(double ox, double oy, double oz);
+    void update_dev(const double4 *pts, size_t n, const Pose &pose) {
+        add_points_dev(pts, n, &pose);
+        remove_far(pose.tx, pose.ty, pose.tz);
+    }
+    long long pointcloud(double *out, size_t cap_points);
+    void load(const int32_t *keys, const int32_t *counts, const double *points, int stride, size_t n_voxels);
+    long long dump(int32_t *keys, int32_t *counts, double *points, size_t cap_voxels);
+
+    // Registration on a device-resident frame.  Returns iterations executed.
+    int register_frame_dev(const double4 *frame, size_t n, const Pose &guess, double max_dist, double kernel, double sem_th,
+                           int max_iters, double est_th, Pose &pose_out);
+    int register_frame_host(const double *xyzl, size_t n, const Pose &guess, double max_dist, double kernel, double sem_th,
+                            int max_iters, double est_th, Pose &pose_out);
+    long long get_correspondences(const double *xyzl, size_t n, double max_dist, double th, double *target_out, uint8_t *matched_out);
+    void normal_equations(const double *xyzl, size_t n, double max_dist, double kernel, double sem_th, double JTJ[36], double JTr[6],
+                          long long *pairs);
+    void nn_stats(const double *xyzl, size_t n, unsigned long long *occupied, unsigned long long *candidates);
+
+    cudaStream_t stream() const { return stream_; }
+    int device() const { return device_; }
+    void profile_enable(bool on);
+    void profile_read(long long *launches, double *ms);
+
+    void comm_init(int rank, int world, const uint8_t id[128]);
+    void comm_destroy();
+
+    // statistics mirror (refreshed by sync_stats)
+    void sync_stats();
+    MapCtrl stats() const { return host_stats_; }
+    double voxel_size() const { return voxel_size_; }
+    int stride() const { return stride_; }
+
+    // scratch upload helper shared with the pipeline: copies n x 4 doubles to a device staging buffer
+    double4 *stage_points(const double *xyzl, size_t n);
+
+private:
+    MapView view();
+    void reserve(size_t extra_points);  // make room for up to `extra_points` new voxels
+    void rebuild_table(uint32_t new_cap);
+    void launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
+                          uint8_t *matched_out);
+    void set_device() const { SAGE_CUDA(cudaSetDevice(device_)); }
+
+    double voxel_size_, max_distance_;
+    int basic_, critical_, stride_;
+    std::vector<int> basic_labels_;
+    int device_;
+    cudaStream_t stream_ = nullptr;
+    int sm_count_ = 148;
+
+    DevBuf<TblEntry> tbl_;
+    uint32_t tbl_cap_ = 0;
+    DevBuf<unsigned long long> blk_key_;
+    DevBuf<int32_t> blk_cnt_;
+    DevBuf<uint32_t> blk_head_, blk_slot_, free_list_;
+    DevBuf<double4> blk_pts_;
+    uint32_t blk_cap_ = 0;
+    DevBuf<MapCtrl> ctrl_;
+    PinBuf<MapCtrl> ctrl_pin_;
+    MapCtrl host_stats_{};
+    size_t hi_bound_ = 0;    // upper bound of ctrl.n_hi
+    size_t live_bound_ = 0;  // upper bound of ctrl.n_live
+
+    // update scratch
+    DevBuf<double4> upd_pts_;
+    DevBuf<uint32_t> upd_slot_, upd_next_;
+    // registration scratch
+    DevBuf<double4> stage_, src_, tgt_;
+    DevBuf<uint8_t> matched_;
+    DevBuf<IcpState> icp_;
+    PinBuf<IcpState> icp_pin_;
+    DevBuf<double> partials_;
+    int nn_grid_ = 0;
+
+    // profiling
+    bool profile_ = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events_;
+    size_t prof_used_ = 0;
+
+    NcclComm *comm_ = nullptr;
+};
+
+}  // namespace sage

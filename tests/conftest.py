@@ -1,0 +1,55 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def cfg():
+    from sage_icp_b200.config import launch_config
+    return launch_config()
+
+
+@pytest.fixture(scope="session")
+def orc():
+    from oracle import oracle_py
+    oracle_py.lib()
+    return oracle_py
+
+
+def pose_delta(a, b):
+    """(translation error [m], rotation angle of Ra^T Rb [rad]) between two wire poses tx,ty,tz,qx,qy,qz,qw."""
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    dt = float(np.linalg.norm(a[:3] - b[:3]))
+    qa, qb = a[3:] / np.linalg.norm(a[3:]), b[3:] / np.linalg.norm(b[3:])
+    d = abs(float(np.dot(qa, qb)))
+    # angle = 2 acos(|<qa,qb>|); use the chord for small angles (acos loses precision near 1)
+    chord = min(np.linalg.norm(qa - qb), np.linalg.norm(qa + qb))
+    ang = 2.0 * np.arcsin(min(1.0, chord / 2.0)) if d > 0.5 else 2.0 * np.arccos(d)
+    return dt, float(ang)
+
+
+POSE_TOL_M = 1e-4    # BASELINE.json north_star: pose within 1e-4 m ...
+POSE_TOL_RAD = 1e-5  # ... and 1e-5 rad of the reference CPU path
+
+
+def map_as_dict(keys, counts, pts):
+    return {tuple(int(v) for v in k): np.array(p[:c]) for k, c, p in zip(keys, counts, pts)}
+
+
+def assert_maps_equal(a, b):
+    """a, b: (keys, counts, pts) dumps.  Same voxel set, same per-voxel points in the same stored order, bit-exact."""
+    da, db = map_as_dict(*a), map_as_dict(*b)
+    assert set(da) == set(db), f"voxel sets differ: {len(da)} vs {len(db)}"
+    for k in da:
+        assert da[k].shape == db[k].shape, f"voxel {k}: {da[k].shape} vs {db[k].shape}"
+        assert np.array_equal(da[k], db[k]), f"voxel {k} differs"

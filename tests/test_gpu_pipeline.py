@@ -1,0 +1,107 @@
+"""GPU parity tests of the pipeline level (Preprocess, VoxelDownsample, Voxelize, RegisterFrame) vs the oracle."""
+import numpy as np
+import pytest
+
+from conftest import POSE_TOL_M, POSE_TOL_RAD, assert_maps_equal, pose_delta
+
+pytestmark = pytest.mark.gpu
+
+
+def _scan(seed, pose=(0.0, 0.0, 0.0), beams=32, az=600):
+    from sage_icp_b200 import synthetic as syn
+    return syn.make_scan(seed, pose, n_beams=beams, n_az=az)
+
+
+def test_preprocess_bit_exact(orc, cfg):
+    import sage_icp_b200 as sg
+    p = sg.SagePipeline(cfg)
+    scan = _scan(1)
+    out = p.preprocess(scan)
+    ref = orc.preprocess(scan, cfg.max_range, cfg.min_range, cfg.label_max_range)
+    assert out.shape == ref.shape and np.array_equal(out, ref)
+    assert (ref[:, 3] == 0).sum() > (scan[:, 3] == 0).sum()  # far labels were zeroed
+    assert len(p.preprocess(np.zeros((0, 4)))) == 0
+
+
+@pytest.mark.parametrize("scale", [0.5, 1.5, 1.0])
+@pytest.mark.parametrize("beams,az", [(32, 600), (64, 1875), (4, 30)])
+def test_voxel_downsample_bit_exact_with_reference_order(orc, cfg, scale, beams, az):
+    """Same survivors AND same output order (robin_map iteration order per group, groups concatenated)."""
+    import sage_icp_b200 as sg
+    p = sg.SagePipeline(cfg)
+    scan = orc.preprocess(_scan(2, beams=beams, az=az), cfg.max_range, cfg.min_range, cfg.label_max_range)
+    out = p.voxel_downsample(scan, scale)
+    ref = orc.voxel_downsample(cfg, scan, scale)
+    assert out.shape == ref.shape
+    assert np.array_equal(out, ref)
+    # points whose label is in no group were dropped
+    assert not np.isin(out[:, 3], [30, 252]).any()
+
+
+def test_voxelize_matches_oracle(orc, cfg):
+    import sage_icp_b200 as sg
+    p = sg.SagePipeline(cfg)
+    op = orc.OraclePipeline(cfg)
+    scan = orc.preprocess(_scan(3), cfg.max_range, cfg.min_range, cfg.label_max_range)
+    s, d = p.voxelize(scan)
+    so, do = op.voxelize(scan)
+    assert np.array_equal(d, do) and np.array_equal(s, so)
+
+
+@pytest.mark.parametrize("variant", ["odometry", "360", "raw"])
+def test_register_frame_sequence_parity(orc, variant):
+    """Full sageICP::RegisterFrame over a short drive: per-frame pose parity, identical query clouds, identical
+    sigma / iteration counts, identical map at the end (oracle in clean-eviction mode)."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    from sage_icp_b200.config import launch_config
+    over = {"odometry": {}, "360": dict(voxel_size_map=1.0, sem_th=0.8), "raw": dict(sem_th=0.2, local_map_range=40.0)}[variant]
+    cfg = launch_config(**over)
+    gp = sg.SagePipeline(cfg)
+    op = orc.OraclePipeline(cfg, evict_faithful=False)
+    n = 25
+    traj = syn.trajectory(n)
+    for i in range(n):
+        scan = syn.make_scan(100 + i, tuple(traj[i]), n_beams=32, n_az=900)
+        pg, ti, ta = gp.register_frame(scan)
+        po, _, _ = op.register_frame(scan)
+        dt, da = pose_delta(pg, po)
+        assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (i, dt, da)
+        assert gp.last_iterations() == op.last_iterations(), i
+        assert gp.last_sigma() == pytest.approx(op.last_sigma(), rel=1e-9, abs=1e-12)
+        assert np.array_equal(gp.last_source(), op.last_source()), i
+        assert np.array_equal(gp.last_frame_downsample(), op.last_frame_downsample()), i
+        assert 0 <= ti <= ta
+    assert np.abs(gp.poses() - op.poses()).max() < 1e-6
+    gm, om = gp.map().dump(), op.map().dump()
+    # map points are pose * point with poses that agree to ~1e-12, so compare with a tolerance
+    from conftest import map_as_dict
+    dg, do = map_as_dict(*gm), map_as_dict(*om)
+    assert set(dg) == set(do)
+    for k in dg:
+        assert dg[k].shape == do[k].shape
+        assert np.allclose(dg[k], do[k], atol=1e-7, rtol=0)
+    # LocalMap(): same point set
+    a, b = gp.local_map(), op.local_map()
+    assert a.shape == b.shape
+
+
+def test_reinitialize(orc, cfg):
+    import sage_icp_b200 as sg
+    gp = sg.SagePipeline(cfg)
+    for i in range(3):
+        gp.register_frame(_scan(i, (0.2 * i, 0, 0)))
+    assert len(gp.poses()) == 3 and gp.map().num_voxels() > 0
+    gp.reinitialize()
+    assert len(gp.poses()) == 0 and gp.map().empty()
+    pose, _, _ = gp.register_frame(_scan(0))
+    assert np.allclose(pose, [0, 0, 0, 0, 0, 0, 1])
+
+
+def test_bad_config_fails_loudly(cfg):
+    import sage_icp_b200 as sg
+    from sage_icp_b200.config import SageConfig, launch_config
+    with pytest.raises(sg.SageError):
+        sg.SagePipeline(SageConfig())  # empty voxel_labels: UB in the reference, error here
+    with pytest.raises(sg.SageError):
+        sg.SagePipeline(launch_config(dynamic_vehicle_filter=True))

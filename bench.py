@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native SAGE-ICP registration hot path.
+
+Metric (BASELINE.json): RegisterFrame scans/s on a 120 k-point labelled scan; NN-kernel GB/s vs the HBM roofline.
+Workload at every N (BASELINE.json configs[1], kernel level): one synthetic 64x1875-ray labelled
+scan fed directly as queries to sage_icp::RegisterFrame (core/Registration.cpp:113-141) against a pre-built 5 M-point
+voxel map, exactly 10 Gauss-Newton iterations (threshold 0 => no early exit).  One "step" = one scan.
+
+  value  : scans/s with the scan already resident in HBM (sage_core_register_frame_device)
+  e2e    : scans/s through the C-ABI call with HOST buffers (pinned): H2D of the scan + D2H of the pose inside
+  N > 1  : the scan's queries are sharded by index over the ranks (sage_shard_range), every rank holds a replica of
+           the map, and the 17 normal-equation sums are all-reduced with NCCL every iteration  => "strong" scaling
+
+--impl reference times the reference's CPU algorithm (the oracle port; the reference itself cannot be built here)
+on the host cores with OpenMP on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MAX_DIST, KERNEL, SEM_TH, ITERS = 3.0, 1.0 / 3.0, 0.4, 10  # sigma = 1.0: 3*sigma, sigma/3 (pipeline/sageICP.cpp:80-85)
+BASIC_LABELS = [40, 44, 48, 49, 50, 70, 72]
+VOXEL_SIZE_MAP, BASIC, CRITICAL = 0.8, 20, 20  # ros/launch/odometry.launch.py:56-60
+
+
+def street_half_length(n_map_points: int) -> float:
+    # calibrated: 10 000 surface samples per metre of street leave ~4 600 map points per metre after the per-voxel
+    # caps, ~18 points/voxel, ~250 voxels per metre (5 M points -> ~275 k voxels < 2^19)
+    return max(120.0, n_map_points / 4600.0 / 2.0)
+
+
+def make_map_points(n_map_points: int) -> np.ndarray:
+    from sage_icp_b200 import synthetic as syn
+    L = street_half_length(n_map_points)
+    chunks, made, seed = [], 0, 1000
+    want = int(2.17 * n_map_points)  # oversampling: the per-voxel caps drop about half of the samples
+    while made < want:
+        m = min(4_000_000, want - made)
+        chunks.append(syn.sample_street_map(m, seed, -L, L))
+        made += m
+        seed += 1
+    return np.concatenate(chunks)
+
+
+def make_queries(step: int, n_beams: int, n_az: int, half_len: float):
+    """Scan `step`, moved into the map frame with a perturbed pose (the ICP initial guess), SURVEY.md §8d."""
+    from sage_icp_b200 import synthetic as syn
+    span = max(0.0, half_len - 110.0)
+    x = (-span + (2 * span) * ((step * 0.61803398875) % 1.0)) if span > 0 else 0.0
+    scan = syn.make_scan(step, (x, 0.0, 0.0), n_beams=n_beams, n_az=n_az)
+    guess = syn.pose7_from_xyyaw((x + 0.3, 0.1, math.radians(1.0)))
+    return scan, guess
+
+
+def algorithmic_bytes(n_q: int, occupied: int, candidates: int) -> float:
+    """N_q*(16 + 27*8) + sum(4 + 16*n_v) + 27*8 per Gauss-Newton iteration."""
+    return n_q * (16 + 27 * 8) + 4.0 * occupied + 16.0 * candidates + 27 * 8
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+            out["sm_mhz"] = float(np.median(busy))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference algorithm, all host threads (OpenMP over the two tbb::parallel_reduce
+    sites).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import oracle_py as orc
+    threads = orc.max_threads()
+    half = street_half_length(args.map_points)
+    omap = orc.OracleMap(VOXEL_SIZE_MAP, 1e9, BASIC, CRITICAL, BASIC_LABELS)
+    omap.add_points(make_map_points(args.map_points))
+    # bounded sample: a fraction of the scan's queries so the whole run ends within minutes
+    times, frac = [], args.cpu_fraction
+    for s in range(args.warmup + args.steps):
+        scan, guess = make_queries(s, args.beams, args.az, half)
+        sub = scan[:: max(1, int(round(1 / frac)))]
+        t = time.perf_counter()
+        omap.register_frame_core(sub, guess, MAX_DIST, KERNEL, SEM_TH, threads=threads, max_iters=ITERS, est_th=0.0)
+        dt = time.perf_counter() - t
+        if s >= args.warmup:
+            times.append(dt * len(scan) / len(sub))  # scaled to the full scan
+    ms = 1e3 * float(np.mean(times))
+    v = 1e3 / ms
+    sample = f"{args.steps} scans, every {max(1, int(round(1 / frac)))}-th query of each 120k-pt scan x {ITERS} GN iters, time scaled to the full scan"
+    print(json.dumps({
+        "impl": "reference", "metric": "RegisterFrame scans/sec (120 k-pt labeled scan)", "value": v, "unit": "scans/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, omap.num_points(), omap.num_voxels()),
+        "cpu_baseline": {"value": v, "unit": "scans/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, map_points, map_voxels):
+    return {"workload": "BASELINE configs[1]: 120k-pt labelled scan as direct queries vs pre-built voxel map, 10 GN iterations "
+                        "(kernel-level sage_icp::RegisterFrame)",
+            "scan_rays": args.beams * args.az, "map_points": int(map_points), "map_voxels": int(map_voxels), "gn_iterations": ITERS,
+            "max_correspondence_distance": MAX_DIST, "kernel": KERNEL, "sem_th": SEM_TH,
+            "l2": "L2 flushed (256 MiB write) between timed steps; each step timed with its own CUDA-event pair",
+            "parallelism": f"query-shard x{args.gpus} + replicated map" if args.gpus > 1 else "single GPU"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--map-points", type=int, default=5_000_000)
+    ap.add_argument("--beams", type=int, default=64)
+    ap.add_argument("--az", type=int, default=1875)
+    ap.add_argument("--cpu-fraction", type=float, default=0.1, help="fraction of each scan the CPU arm times")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import sage_icp_b200 as sg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if sg.device_count() < 1:
+        raise SystemExit("bench.py: no sm_100 device; sage_icp_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    # ---- untimed setup: replicated map, scans ------------------------------------------------------------
+    half = street_half_length(args.map_points)
+    map_pts = make_map_points(args.map_points)
+    gmap = sg.SageMap(VOXEL_SIZE_MAP, 1e9, BASIC, CRITICAL, BASIC_LABELS, device=local)
+    gmap.add_points(map_pts)
+    n_map_points, n_map_voxels = gmap.num_points(), gmap.num_voxels()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(sg.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        gmap.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+
+    total = args.warmup + args.steps
+    scans, guesses, shards_dev, shards_pin = [], [], [], []
+    for s in range(total):
+        scan, guess = make_queries(s, args.beams, args.az, half)
+        b, e = sg.shard_range(len(scan), rank, world)
+        shard = np.ascontiguousarray(scan[b:e])
+        scans.append(scan); guesses.append(guess)
+        shards_dev.append(torch.from_numpy(shard).cuda())
+        shards_pin.append(torch.from_numpy(shard).pin_memory())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.ExternalStream(gmap.stream(), device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn):
+        """K steps after W warm-ups; every step bracketed by CUDA events on the library's stream; L2 flushed between."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for s in range(args.warmup):
+            fn(s)
+        barrier()
+        l0 = sg.launch_count()
+        wall0 = time.perf_counter()
+        for k in range(args.steps):
+            flush.fill_(k & 0xff)
+            barrier()
+            ev[k][0].record(stream)
+            fn(args.warmup + k)
+            ev[k][1].record(stream)
+        barrier()
+        wall = time.perf_counter() - wall0
+        ms = [a.elapsed_time(b) for a, b in ev]
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()), sg.launch_count() - l0
+
+    def step_resident(s):
+        gmap.register_frame_device(shards_dev[s].data_ptr(), shards_dev[s].shape[0], guesses[s], MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
+
+    def step_e2e(s):
+        gmap.register_frame(shards_pin[s].numpy(), guesses[s], MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
+
+    # ---- timed: resident ----------------------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    tot_ms, launches = timed_loop(step_resident)
+    clocks = sampler.stop() if sampler else None
+    # ---- timed: end to end through the host-buffer C-ABI call ---------------------------------------------
+    e2e_ms, _ = timed_loop(step_e2e)
+    # ---- roofline pass: per-kernel CUDA events inside the library (same steps) ----------------------------
+    gmap.profile_enable(True)
+    for s in range(args.warmup, total):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        step_resident(s)
+    n_kernels, kernel_ms = gmap.profile_read()
+    gmap.profile_enable(False)
+    alg = []
+    for s in range(args.warmup, total):
+        q = shards_dev[s].cpu().numpy().copy()
+        # statistics at the positions the first iteration sees (guess applied), counted exactly on the device map
+        qq = q.copy()
+        g = guesses[s]
+        yaw = 2.0 * math.atan2(g[5], g[6])
+        c, sn = math.cos(yaw), math.sin(yaw)
+        qq[:, 0] = c * q[:, 0] - sn * q[:, 1] + g[0]
+        qq[:, 1] = sn * q[:, 0] + c * q[:, 1] + g[1]
+        qq[:, 2] = q[:, 2] + g[2]
+        occ, cand = gmap.nn_stats(qq)
+        alg.append(algorithmic_bytes(len(qq), occ, cand))
+    bytes_per_launch = float(np.mean(alg))
+    peak, peak_src = measured_peak_gbs()
+    achieved = bytes_per_launch * n_kernels / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch of the same kernel from an ncu --set full capture
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (oracle port), bounded sample --------------------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle_py as orc
+        threads = orc.max_threads()
+        omap = orc.OracleMap(VOXEL_SIZE_MAP, 1e9, BASIC, CRITICAL, BASIC_LABELS)
+        omap.add_points(map_pts)
+        stride = max(1, int(round(1 / args.cpu_fraction)))
+        scan, guess = scans[args.warmup], guesses[args.warmup]
+        sub = scan[::stride]
+        t = time.perf_counter(); pose_c, _ = omap.register_frame_core(sub, guess, MAX_DIST, KERNEL, SEM_TH, threads=threads, max_iters=ITERS, est_th=0.0)
+        t_all = (time.perf_counter() - t) * len(scan) / len(sub)
+        sub1 = scan[:: stride * 4]
+        t = time.perf_counter(); omap.register_frame_core(sub1, guess, MAX_DIST, KERNEL, SEM_TH, threads=1, max_iters=ITERS, est_th=0.0)
+        t_one = (time.perf_counter() - t) * len(scan) / len(sub1)
+        # parity spot check on the sample (same sub-scan through the GPU path)
+        pose_g, _ = gmap.register_frame(sub, guess, MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
+        cpu = {"value": 1.0 / t_all, "unit": "scans/s", "cores": threads, "kind": "port",
+               "sample": f"1 scan, every {stride}-th query x {ITERS} GN iters on the same {n_map_points}-pt map, time scaled to 120k queries",
+               "single_thread_value": 1.0 / t_one,
+               "pose_delta_vs_gpu_m": float(np.linalg.norm(pose_g[:3] - pose_c[:3]))}
+
+    n_scans = args.steps
+    line = {
+        "metric": "RegisterFrame scans/sec (120 k-pt labeled scan)", "value": n_scans / (tot_ms * 1e-3), "unit": "scans/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_map_points, n_map_voxels),
+        "e2e": {"value": n_scans / (e2e_ms * 1e-3), "unit": "scans/s", "h2d_bytes_per_step": int(shards_pin[0].numel() * 8),
+                "d2h_bytes_per_step": 7 * 8 + 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "nn_normal_eq_kernel (correspondence search + normal equations, 1 launch per GN iteration)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": int(n_kernels),
+                     "avg_launch_us": 1e3 * kernel_ms / max(1, n_kernels)},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

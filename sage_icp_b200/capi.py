@@ -17,7 +17,7 @@ import numpy as np
 from .config import ConfigPOD, SageConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "lib", "libsage_icp_b200.so")
+_LIB = os.environ.get("SAGE_ICP_LIB") or os.path.join(_HERE, "lib", "libsage_icp_b200.so")  # SAGE_ICP_LIB: tuning builds
 _HEADER = os.path.join(os.path.dirname(_HERE), "include", "sage_icp_b200.h")
 
 _dp = C.POINTER(C.c_double)
@@ -192,6 +192,14 @@ class SageMap:
         pts = _c64(pts); o, c = C.c_uint64(), C.c_uint64()
         self._chk(self.L.sage_map_nn_stats(self.h, _d(pts), C.c_size_t(len(pts)), C.byref(o), C.byref(c)), "sage_map_nn_stats")
         return int(o.value), int(c.value)
+
+    def search_work(self, pts, max_dist: float, th: float) -> Tuple[int, int, int, int]:
+        """(records scanned, table probes, queries re-ranked in f64, queries handed to the warp-per-query kernel) of one
+        correspondence pass."""
+        pts = _c64(pts); a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._chk(self.L.sage_map_search_work(self.h, _d(pts), C.c_size_t(len(pts)), C.c_double(max_dist), C.c_double(th),
+                                              C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "sage_map_search_work")
+        return int(a.value), int(b.value), int(c.value), int(d.value)
 
     def normal_equations(self, pts, max_dist: float, kernel: float, sem_th: float):
         pts = _c64(pts); JTJ = np.zeros((6, 6)); JTr = np.zeros(6); n = C.c_int64()

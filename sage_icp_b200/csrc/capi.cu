@@ -248,6 +248,16 @@ int sage_map_nn_stats(sage_map *m, const double *xyzl, size_t n, uint64_t *occup
         return 0;
     });
 }
+int sage_map_search_work(sage_map *m, const double *xyzl, size_t n, double max_dist, double th, uint64_t *scanned, uint64_t *probes,
+                         uint64_t *exact, uint64_t *deferred) {
+    return (int)guarded([&] {
+        unsigned long long a = 0, b = 0, c = 0, d = 0;
+        m->impl->search_work(xyzl, n, max_dist, th, &a, &b, &c, &d);
+        *scanned = a, *probes = b, *exact = c;
+        if (deferred) *deferred = d;
+        return 0;
+    });
+}
 int sage_core_register_frame(sage_map *m, const double *frame, size_t n, const double guess[7], double max_dist, double kernel,
                              double sem_th, int max_iters, double est_th, double pose_out[7], int *iters_out) {
     return (int)guarded([&] {
@@ -295,6 +305,8 @@ int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms) {
         return 0;
     });
 }
+// development aid, deliberately not in the public header
+size_t sage_debug_timeline(sage_map *m, unsigned long long *out, size_t cap) { return m->impl->debug_timeline(out, cap); }
 int64_t sage_launch_count(void) { return g_launches.load(); }
 
 int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end) {

@@ -120,6 +120,24 @@ SAGE_HD int trunc_div(double a, double b) {
 #endif
 }
 
+// 16-byte search record of a map point: f32 offsets from the voxel origin (key * voxel_size, so |offset| < voxel_size
+// and the rounding error is <= 2^-24 * voxel_size ~ 5e-8 m for 0.8 m voxels) + the label.  The label is stored only when
+// it is an integer the f32 holds exactly; anything else becomes NaN, which sends every query that meets the record
+// down the exact f64 path.  The search kernel ranks candidates on these records and proves the winner unique within a
+// rigorous error band, or re-ranks in f64 on the 32-byte exact records (registration.cu).
+#ifdef __CUDACC__
+__device__ __forceinline__ float hot_offset(double coord, int key, double voxel_size) {
+    return __double2float_rn(__dsub_rn(coord, __dmul_rn((double)key, voxel_size)));
+}
+__device__ __forceinline__ float hot_label(double label) {
+    const float f = __double2float_rn(label);
+    return ((double)f == label && truncf(f) == f && fabsf(f) < 8388608.0f) ? f : __int_as_float(0x7fc00000);
+}
+__device__ __forceinline__ float4 hot_record(const double4 &p, int kx, int ky, int kz, double voxel_size) {
+    return make_float4(hot_offset(p.x, kx, voxel_size), hot_offset(p.y, ky, voxel_size), hot_offset(p.z, kz, voxel_size), hot_label(p.w));
+}
+#endif
+
 // One open-addressing table entry: packed voxel key, block id, and a mirror of the block's point count so a
 // probe answers "where and how many" with a single 16-byte load.
 struct __align__(16) TblEntry {
@@ -153,6 +171,7 @@ struct IcpState {
     int done;
     unsigned ticket;  // last-block election
     unsigned long long stat_occupied, stat_candidates;
+    unsigned long long stat_scanned, stat_probes, stat_exact, stat_heavy;  // search-kernel work counters (counting launches only)
 };
 
 }  // namespace sage

@@ -7,12 +7,20 @@
 //   the loop body of RegisterFrame       core/Registration.cpp:127-138
 // Correspondences are never materialised: the winner of each query feeds the 16 normal-equation sums directly.
 //
-// Parallel shape: a group of G lanes (G = 32 by default) owns Q <= G queries per pass; lane j keeps query j's
-// transformed point, and the group scans the 27-voxel neighbourhood of one query at a time: lanes probe the
-// open-addressed table in parallel (one 16-byte entry load answers block id + count), then read the voxel's
-// 32-byte point records with coalesced 256-bit loads, rank them in f64 with exactly the reference's operation
-// order, and elect the winner with redux (__reduce_min_sync) on (metric, enumeration order).
+// Search strategy (results are IDENTICAL to the reference's f64 scan of all 27 voxels):
+//   1. A group of G lanes owns G queries per pass; lane j keeps query j (f64, transformed in place exactly as the
+//      reference does) and the group searches one query at a time.
+//   2. Candidates are ranked on 16-byte f32 voxel-relative records (common.cuh: hot_record) — half the bytes of the
+//      reference's Vector4d and f32 arithmetic.  Every f32 metric carries a rigorous error bound e(D).
+//   3. Home voxel first; a neighbour voxel is probed and scanned only if a conservative lower bound of the metric over
+//      its bounding box does not already exceed the best metric found (exact: such a voxel cannot hold the arg-min,
+//      nor tie with it).
+//   4. The f32 arg-min is accepted only if no other candidate lies within the error band; otherwise (rare: ~1e-4 of
+//      the queries) the query is re-ranked by nn_exact(): the reference's own f64 operation sequence over all 27 voxels in
+//      enumeration order with the strict-'<' first-wins rule (core/VoxelHashMap.cpp:57-63,81-93).
+//   5. The winner's exact f64 record is fetched for the acceptance test and the residual.
 #include <cfloat>
+#include <cstdlib>
 
 #include "nccl_shim.cuh"
 #include "voxel_map.cuh"
@@ -21,17 +29,23 @@ namespace sage {
 
 constexpr int kNnThreads = 256;
 constexpr int kSums = 17;
+constexpr int kDbg = 12;  // debug timeline stamps per block
+
 
 struct IterParams {
     const TblEntry *tbl;
     uint32_t mask;
     const double4 *blk_pts;
+    const float4 *blk_hot;
     int stride;
     double voxel_size;
     double4 *src;
     uint32_t n;
-    uint32_t chunk;  // Q: queries per group per pass (1..G)
     double max_dist, kern, sem_th;
+    // f32 search constants (host-computed): voxel size, metric scale for compatible labels, error model
+    // e(D) = err_a * sqrt(D) + err_b * D + err_c on a metric whose squared distance is D, lower-bound shrink + margin
+    float vs32, th32, smin32, inv_smin32, err_scale, err_a, err_b, err_c, box_margin;
+    int fast_ok;  // 0: sem_th outside (0, inf) or non-finite -> every query takes the exact path
     IcpState *st;
     double *partials;
     double4 *tgt_out;
@@ -39,6 +53,8 @@ struct IterParams {
     int apply_est;
     int solve;
     int respect_done;
+    int light_probes;  // neighbour probes a query may spend in the thread-per-query phase before it is deferred
+    unsigned long long *dbg;  // optional per-block timeline (tools/perf_probe.py): 4 globaltimer stamps per block + 4 global
 };
 
 __device__ __forceinline__ double4 ldg256(const double4 *p) {
@@ -69,6 +85,11 @@ __device__ __forceinline__ bool tbl_find(const TblEntry *tbl, uint32_t mask, uns
     }
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ double shfl_d(unsigned mask, double v, int lane) { return __shfl_sync(mask, v, lane); }
 
 // One Gauss-Newton step from the reduced sums: x = LDLT(JTJ)^-1 (-JTr); est = exp(x); T_icp = est * T_icp;
@@ -111,6 +132,7 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->done = (max_iters <= 0);
     st->ticket = 0;
     st->stat_occupied = st->stat_candidates = 0;
+    st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = 0;
 }
 
 __global__ void icp_solve_kernel(IcpState *st) {
@@ -118,173 +140,504 @@ __global__ void icp_solve_kernel(IcpState *st) {
     icp_solve_step(st);
 }
 
-template <int G, bool STATS>
-__global__ void __launch_bounds__(kNnThreads) nn_normal_eq_kernel(IterParams p) {
-    __shared__ double s_red[kNnThreads / 32][kSums];
+// ---------------------------------------------------------------------------------------------
+// Exact path: the reference's f64 scan of all 27 voxels in enumeration order (x outer, y, z inner; stored order inside
+// a voxel), strict '<' from DBL_MAX.  Group-cooperative; returns the winner's record index (block * stride + slot) or
+// kNil when the neighbourhood holds no point, identical on every lane of the group.
+template <int G>
+__device__ __noinline__ uint32_t nn_exact(const IterParams &p, unsigned gmask, int gl, double cx, double cy, double cz, double cl,
+                                          int ckx, int cky, int ckz) {
+    const int cql = __double2int_rz(cl);
+    const double th = p.sem_th;
+    double best = DBL_MAX;  // closest_distance2 init, core/VoxelHashMap.cpp:81
+    uint32_t best_ord = 0xffffffffu, best_idx = kNil;
+#pragma unroll 1
+    for (int pr0 = 0; pr0 < 27; pr0 += G) {
+        const int pr = pr0 + gl;
+        bool found = false;
+        uint32_t blk = 0, cnt = 0;
+        if (pr < 27) {
+            const int nx = ckx + pr / 9 - 1, ny = cky + (pr / 3) % 3 - 1, nz = ckz + pr % 3 - 1;
+            if (key_in_range(nx, ny, nz)) found = tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), blk, cnt) && cnt > 0;
+        }
+        unsigned fm = __ballot_sync(gmask, found) & gmask;
+        while (fm) {
+            const int l = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const uint32_t b = __shfl_sync(gmask, blk, l), c = __shfl_sync(gmask, cnt, l);
+            const uint32_t ord_base = (uint32_t)(pr0 + (l & (G - 1))) << 16;  // voxel enumeration index : slot
+            const double4 *vp = p.blk_pts + (size_t)b * p.stride;
+            for (uint32_t j = gl; j < c; j += G) {
+                const double4 nb = ldg256(vp + j);
+                const double dx = __dsub_rn(nb.x, cx), dy = __dsub_rn(nb.y, cy), dz = __dsub_rn(nb.z, cz);
+                double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                // semantic metric, core/VoxelHashMap.cpp:87-88
+                if (__double2int_rz(nb.w) == cql || __double2int_rz(__dmul_rn(nb.w, cl)) == 0) d = __dmul_rn(d, th);
+                if (d < best) best = d, best_ord = ord_base + j, best_idx = b * (uint32_t)p.stride + j;
+            }
+        }
+    }
+    // group arg-min on (metric, enumeration order): strict '<' => first minimum wins (core/VoxelHashMap.cpp:89).
+    // Plain shuffle butterfly on f64 (this path is rare, and it stays correct for a negative sem_th).
+#pragma unroll
+    for (int s = G / 2; s > 0; s >>= 1) {
+        const double om = __shfl_xor_sync(gmask, best, s);
+        const uint32_t oo = __shfl_xor_sync(gmask, best_ord, s), oi = __shfl_xor_sync(gmask, best_idx, s);
+        if (oo != 0xffffffffu && (best_ord == 0xffffffffu || om < best || (om == best && oo < best_ord))) best = om, best_ord = oo, best_idx = oi;
+    }
+    return best_ord == 0xffffffffu ? kNil : best_idx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// f32 ranking helpers
+
+// e(D): bound on |m32 - m| for a metric whose squared distance is <= D (derivation in DESIGN.md §4)
+__device__ __forceinline__ float err_of(const IterParams &p, float D) { return p.err_scale * (p.err_a * sqrtf(D) + p.err_b * D) + p.err_c; }
+// A voxel whose metric lower bound exceeds this cannot hold the f64 arg-min or tie it: exact best-so-far <= gb + e(gb/smin)
+__device__ __forceinline__ float prune_bound(const IterParams &p, float gb) { return gb + 2.0f * err_of(p, gb * p.inv_smin32); }
+// The f64 arg-min j* satisfies m32(j*) <= gm + e(D_min) + e(D_j*) with D_min <= gm/smin, D_j* <= (gm + e(D_min))/smin
+__device__ __forceinline__ float band_limit(const IterParams &p, float gm) {
+    const float e1 = err_of(p, gm * p.inv_smin32);
+    return gm + 1.01f * (e1 + err_of(p, (gm + e1) * p.inv_smin32));
+}
+
+// rank one search record against the query at (rx, ry, rz) relative to the record's voxel origin
+__device__ __forceinline__ void rank_record(const float4 h, uint32_t idx, float rx, float ry, float rz, float qlf, float th32, float &min1,
+                                            float &min2, uint32_t &idx1, bool &odd) {
+    const float dx = h.x - rx, dy = h.y - ry, dz = h.z - rz;
+    const float D = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    // labels are exact integers here (hot_label): int(l_n) == int(l_q) || int(l_n * l_q) == 0  <=>  equal or one is 0
+    const bool compat = (h.w == qlf) || (h.w * qlf == 0.0f);
+    odd |= (h.w != h.w);  // non-integer label stored as NaN: the f32 ranking is not valid for this query
+    const float m = compat ? D * th32 : D;
+    if (m < min1) {
+        min2 = min1, min1 = m, idx1 = idx;
+    } else {
+        min2 = fminf(min2, m);
+    }
+}
+
+// one thread scans one voxel (8 independent 16-byte loads in flight)
+#ifndef SAGE_SCAN_UNROLL
+#define SAGE_SCAN_UNROLL 4
+#endif
+#ifndef SAGE_LIGHT_MINB
+#define SAGE_LIGHT_MINB 4
+#endif
+__device__ __forceinline__ void scan_voxel_thread(const float4 *__restrict__ hot, uint32_t base_idx, uint32_t cnt, float rx, float ry, float rz,
+                                                  float qlf, float th32, float &min1, float &min2, uint32_t &idx1, bool &odd) {
+    constexpr int U = SAGE_SCAN_UNROLL;
+    // a voxel's records span up to 5 128-byte lines: start them all now so that the loop below misses L1 only once
+    for (uint32_t l = 8; l < cnt; l += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(hot + base_idx + l));
+    uint32_t j = 0;
+    for (; j + U <= cnt; j += U) {
+        float4 h[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) h[u] = __ldg(hot + base_idx + j + u);
+#pragma unroll
+        for (int u = 0; u < U; ++u) rank_record(h[u], base_idx + j + u, rx, ry, rz, qlf, th32, min1, min2, idx1, odd);
+    }
+    if (j < cnt) {
+        float4 h[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j + u < cnt) h[u] = __ldg(hot + base_idx + j + u);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (j + u < cnt) rank_record(h[u], base_idx + j + u, rx, ry, rz, qlf, th32, min1, min2, idx1, odd);
+    }
+}
+
+// Per-axis squared, scaled distance from the query (offset r from its home voxel's origin, home key k) to the boxes of
+// the two face neighbours k-1 / k+1.  A voxel with key k holds coordinates in [0, vs) (k > 0), (-vs, vs) (k = 0) or
+// (-vs, 0] (k < 0) relative to k * vs (truncation toward zero); `margin` absorbs every rounding.
+__device__ __forceinline__ void axis_bounds(float r, int k, float vs, float margin, float smin, float &sm, float &sp) {
+    const float em = fmaxf((r + vs) - (k - 1 >= 0 ? vs : 0.0f) - margin, 0.0f);
+    const float ep = fmaxf((k + 1 <= 0 ? -vs : 0.0f) - (r - vs) - margin, 0.0f);
+    sm = smin * em * em, sp = smin * ep * ep;
+}
+
+// residual, Geman-McClure weight and the 16 sums + pair count of one accepted pair, into column t of the shared sums
+// (core/Registration.cpp:62-70,79-85)
+template <int COLS>
+__device__ __forceinline__ void accumulate_pair(double (*s_acc)[COLS], int t, double kern, double sx, double sy, double sz, double tx,
+                                                double ty, double tz) {
+    const double rx = sx - tx, ry = sy - ty, rz = sz - tz;
+    const double r2 = (rx * rx + ry * ry) + rz * rz;
+    const double den = kern + r2;
+    const double w = (kern * kern) / (den * den);
+    const double wx = w * sx, wy = w * sy, wz = w * sz;
+    s_acc[0][t] += w;
+    s_acc[1][t] += wx, s_acc[2][t] += wy, s_acc[3][t] += wz;
+    s_acc[4][t] += wx * sx, s_acc[5][t] += wy * sy, s_acc[6][t] += wz * sz;
+    s_acc[7][t] += wx * sy, s_acc[8][t] += wx * sz, s_acc[9][t] += wy * sz;
+    s_acc[10][t] += w * rx, s_acc[11][t] += w * ry, s_acc[12][t] += w * rz;
+    s_acc[13][t] += w * (sy * rz - sz * ry), s_acc[14][t] += w * (sz * rx - sx * rz), s_acc[15][t] += w * (sx * ry - sy * rx);
+    s_acc[16][t] += 1.0;
+}
+
+// acceptance test on the exact records: ||n - p|| < max_correspondance_distance (core/VoxelHashMap.cpp:111)
+__device__ __forceinline__ bool accept_pair(const double4 &nb, double sx, double sy, double sz, double max_dist) {
+    const double dx = __dsub_rn(nb.x, sx), dy = __dsub_rn(nb.y, sy), dz = __dsub_rn(nb.z, sz);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return __dsqrt_rn(d2) < max_dist;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative f32 search of one query over all 27 voxels: lane = voxel in the reference's enumeration order (all 27
+// probed at once), found voxels scanned four at a time by the whole warp, same ranking + error band; ambiguous queries
+// fall through to nn_exact<32>.  Returns the winner's record index or kNil, identical on every lane.
+template <bool COUNT>
+__device__ __noinline__ uint32_t search_query_warp(const IterParams &p, int lane, const double4 s, unsigned long long &n_scanned,
+                                                   unsigned long long &n_probes, unsigned long long &n_exact) {
+    const double vs = p.voxel_size;
+    const float vs32 = p.vs32, th32 = p.th32;
+    const float INF = __int_as_float(0x7f800000);
+    const unsigned FULL = 0xffffffffu;
+    const int kx = trunc_div(s.x, vs), ky = trunc_div(s.y, vs), kz = trunc_div(s.z, vs);
+    const float bx = hot_offset(s.x, kx, vs), by = hot_offset(s.y, ky, vs), bz = hot_offset(s.z, kz, vs);
+    const float qlf = hot_label(s.w);
+    bool odd = !p.fast_ok || (qlf != qlf) || !(fabsf(bx) <= 2.0f * vs32 && fabsf(by) <= 2.0f * vs32 && fabsf(bz) <= 2.0f * vs32);
+    uint32_t widx = kNil;
+    if (!odd) {
+        bool found = false;
+        uint32_t blk = 0, cnt = 0;
+        if (lane < 27) {
+            const int nx = kx + lane / 9 - 1, ny = ky + (lane / 3) % 3 - 1, nz = kz + lane % 3 - 1;
+            if (key_in_range(nx, ny, nz)) found = tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), blk, cnt) && cnt > 0;
+        }
+        unsigned fm = __ballot_sync(FULL, found);
+        if (COUNT && lane == 0) n_probes += 27;
+        float min1 = INF, min2 = INF;
+        uint32_t idx1 = kNil;
+        while (fm) {  // four voxels per round: their loads are independent
+            int l[4];
+            uint32_t b[4], c[4];
+            float x[4], y[4], z[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                l[u] = fm ? __ffs(fm) - 1 : -1;
+                fm &= fm - 1;  // 0 & anything stays 0
+                const int src = l[u] < 0 ? 0 : l[u];
+                b[u] = __shfl_sync(FULL, blk, src) * (uint32_t)p.stride;
+                c[u] = l[u] < 0 ? 0u : __shfl_sync(FULL, cnt, src);
+                x[u] = bx - (float)(src / 9 - 1) * vs32, y[u] = by - (float)((src / 3) % 3 - 1) * vs32, z[u] = bz - (float)(src % 3 - 1) * vs32;
+            }
+            const uint32_t cmax = max(max(c[0], c[1]), max(c[2], c[3]));
+            for (uint32_t j = lane; j < cmax; j += 32) {
+                float4 h[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j < c[u]) h[u] = __ldg(p.blk_hot + b[u] + j);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j < c[u]) rank_record(h[u], b[u] + j, x[u], y[u], z[u], qlf, th32, min1, min2, idx1, odd);
+            }
+            if (COUNT && lane == 0) n_scanned += c[0] + c[1] + c[2] + c[3];
+        }
+        odd = __any_sync(FULL, odd);
+        if (!odd) {
+            const float gm = __uint_as_float(__reduce_min_sync(FULL, __float_as_uint(min1)));
+            if (gm < INF) {
+                const float T = band_limit(p, gm);
+                const unsigned in1 = __ballot_sync(FULL, min1 <= T), in2 = __ballot_sync(FULL, min2 <= T);
+                if (__popc(in1) == 1 && in2 == 0)
+                    widx = __shfl_sync(FULL, idx1, __ffs(in1) - 1);
+                else
+                    odd = true;
+            }
+        }
+    }
+    if (odd) {
+        widx = nn_exact<32>(p, FULL, lane, s.x, s.y, s.z, s.w, kx, ky, kz);
+        if (COUNT && lane == 0) n_exact += 1;
+    }
+    return widx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The search kernel: one launch per Gauss-Newton iteration.
+// Light phase — one thread per query: home voxel, then neighbours nearest-bounding-box first with the prune bound
+// re-tightened after every voxel, at most `light_probes` neighbour probes.  A query that still has open neighbours after
+// that (far from every map point: it has to look at most of its 27 voxels) is put on the block's deferred list.
+// Heavy phase — the block's 8 warps share the deferred queries, one warp per query (search_query_warp).
+// Queries are dealt to warps in chunks of 32 consecutive points, chunk c to block c % grid, so every block sees a
+// cross-section of the scan and the expensive regions (sparse, far from the sensor) spread over all SMs.
+#define SAGE_STAMP(i) do { if (p.dbg && pass == 0 && warp == 0) { __syncwarp(); if (lane == 0) p.dbg[kDbg * blockIdx.x + (i)] = gtime(); } } while (0)
+template <bool COUNT>
+__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(IterParams p) {
+    constexpr int kWarps = kNnThreads / 32;
+    // per-thread running sums live in shared memory (s_acc[k][thread]) so that the search loop keeps its registers
+    __shared__ double s_acc[kSums][kNnThreads];
+    __shared__ Pose s_est;
+    __shared__ uint32_t s_cnt[kWarps];
+    __shared__ uint32_t s_list[kNnThreads];
     __shared__ int s_last;
     IcpState *st = p.st;
     if (p.respect_done && st->done) return;
-
-    const Pose est = st->est;
-    const int lane = threadIdx.x & 31, gl = lane & (G - 1), gbase = lane - gl;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
-    const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) / G, n_groups = gridDim.x * blockDim.x / G;
-    const uint32_t Q = p.chunk;
-    const double vs = p.voxel_size, th = p.sem_th;
-
-    double acc[16];
+    if (threadIdx.x == 0) s_est = st->est;
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x] = gtime();
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-    double npairs = 0.0;
-    unsigned long long occ = 0, cand = 0;
+    for (int k = 0; k < kSums; ++k) s_acc[k][threadIdx.x] = 0.0;
+    __syncthreads();
 
-    for (uint32_t base = group * Q; base < p.n; base += n_groups * Q) {
-        const uint32_t q = base + gl;
-        const bool valid = gl < Q && q < p.n;
-        double sx = 0, sy = 0, sz = 0, sl = 0;
-        if (valid) {
-            double4 s = ld256(p.src + q);
-            if (p.apply_est) {
-                pose_act(est, s.x, s.y, s.z, sx, sy, sz);
-                sl = s.w;
-                st256(p.src + q, make_double4(sx, sy, sz, sl));
-            } else {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double vs = p.voxel_size;
+    const float vs32 = p.vs32, th32 = p.th32;
+    const float INF = __int_as_float(0x7f800000);
+    unsigned long long n_scanned = 0, n_probes = 0, n_exact = 0, n_heavy = 0;
+
+    const uint32_t n_chunks = (p.n + 31) / 32, chunks_per_pass = gridDim.x * kWarps;
+    const uint32_t passes = (n_chunks + chunks_per_pass - 1) / chunks_per_pass;  // same for every warp of every block
+    for (uint32_t pass = 0; pass < passes; ++pass) {
+        const uint32_t chunk = (pass * kWarps + warp) * gridDim.x + blockIdx.x;
+        const uint32_t wbase = chunk * 32u, q = wbase + lane;
+        const bool valid = chunk < n_chunks && q < p.n;
+        int kx, ky, kz;
+        float bx, by, bz, qlf;
+        {
+            double sx = 0, sy = 0, sz = 0, sl = 0;
+            if (valid) {
+                const double4 s = ld256(p.src + q);
                 sx = s.x, sy = s.y, sz = s.z, sl = s.w;
+                if (p.apply_est) {  // source <- est * source, in place (core/Registration.cpp:133)
+                    const Pose est = s_est;
+                    pose_act(est, s.x, s.y, s.z, sx, sy, sz);
+                    st256(p.src + q, make_double4(sx, sy, sz, sl));
+                }
             }
+            kx = trunc_div(sx, vs), ky = trunc_div(sy, vs), kz = trunc_div(sz, vs);
+            // query relative to its home voxel's origin, and its label, in f32
+            bx = hot_offset(sx, kx, vs), by = hot_offset(sy, ky, vs), bz = hot_offset(sz, kz, vs);
+            qlf = hot_label(sl);
         }
-        const int kx = trunc_div(sx, vs), ky = trunc_div(sy, vs), kz = trunc_div(sz, vs);
-        const int ql = __double2int_rz(sl);
-        double tx = 0, ty = 0, tz = 0, tl = 0;
-        bool ok = false;
+        // `odd` marks queries the f32 ranking cannot serve
+        bool odd = !p.fast_ok || (qlf != qlf) || !(fabsf(bx) <= 2.0f * vs32 && fabsf(by) <= 2.0f * vs32 && fabsf(bz) <= 2.0f * vs32);
+        bool heavy = false;
+        uint32_t widx = kNil;
+        __syncwarp();  // the transformed points of this pass are visible to the whole warp (the exact path re-reads them)
+        SAGE_STAMP(4);
 
-        const int nq = min(Q, p.n - base);
-        for (int i = 0; i < nq; ++i) {
-            const int from = gbase + i;
-            const double cx = shfl_d(gmask, sx, from), cy = shfl_d(gmask, sy, from), cz = shfl_d(gmask, sz, from);
-            const double cl = shfl_d(gmask, sl, from);
-            const int ckx = __shfl_sync(gmask, kx, from), cky = __shfl_sync(gmask, ky, from), ckz = __shfl_sync(gmask, kz, from);
-            const int cql = __shfl_sync(gmask, ql, from);
-
-            double best = DBL_MAX;  // closest_distance2 init, core/VoxelHashMap.cpp:81
-            uint32_t best_ord = 0xffffffffu, best_idx = 0, ord_base = 0;
+        float min1 = INF, min2 = INF;
+        uint32_t idx1 = kNil;
+        uint32_t hblk = 0, hcnt = 0;
+        const bool hfound = valid && !odd && key_in_range(kx, ky, kz) && tbl_find(p.tbl, p.mask, pack_key(kx, ky, kz), hblk, hcnt) && hcnt > 0;
+        SAGE_STAMP(5);
+        if (hfound) {
+            scan_voxel_thread(p.blk_hot, hblk * (uint32_t)p.stride, hcnt, bx, by, bz, qlf, th32, min1, min2, idx1, odd);
+            if (COUNT) n_scanned += hcnt;
+        }
+        SAGE_STAMP(6);
+        if (valid && !odd) {
+            if (COUNT) n_probes += 1;
+            // ---- neighbours, nearest bounding box first, while one can still beat the best so far ----
+            float sxm, sxp, sym, syp, szm, szp;
+            axis_bounds(bx, kx, vs32, p.box_margin, p.smin32, sxm, sxp);
+            axis_bounds(by, ky, vs32, p.box_margin, p.smin32, sym, syp);
+            axis_bounds(bz, kz, vs32, p.box_margin, p.smin32, szm, szp);
+            uint32_t visited = 1u << 13;  // bit (ox+1)*9 + (oy+1)*3 + (oz+1): the reference's enumeration index
+            float bound = prune_bound(p, min1);
+            int budget = p.light_probes;
 #pragma unroll 1
-            for (int pr0 = 0; pr0 < 27; pr0 += G) {
-                const int pr = pr0 + gl;
-                bool found = false;
-                uint32_t blk = 0, cnt = 0;
-                if (pr < 27) {
-                    // enumeration order x outer, y, z inner (core/VoxelHashMap.cpp:57-63)
-                    const int nx = ckx + pr / 9 - 1, ny = cky + (pr / 3) % 3 - 1, nz = ckz + pr % 3 - 1;
-                    if (key_in_range(nx, ny, nz)) found = tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), blk, cnt) && cnt > 0;
-                }
-                unsigned fm = __ballot_sync(gmask, found) & gmask;
-                if (STATS && gl == 0) occ += __popc(fm);
-                while (fm) {
-                    const int l = __ffs(fm) - 1;
-                    fm &= fm - 1;
-                    const uint32_t b = __shfl_sync(gmask, blk, l), c = __shfl_sync(gmask, cnt, l);
-                    const double4 *vp = p.blk_pts + (size_t)b * p.stride;
-                    for (uint32_t j = gl; j < c; j += G) {
-                        const double4 nb = ldg256(vp + j);
-                        const double dx = __dsub_rn(nb.x, cx), dy = __dsub_rn(nb.y, cy), dz = __dsub_rn(nb.z, cz);
-                        double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        // semantic metric, core/VoxelHashMap.cpp:87-88
-                        if (__double2int_rz(nb.w) == cql || __double2int_rz(__dmul_rn(nb.w, cl)) == 0) d = __dmul_rn(d, th);
-                        if (d < best) best = d, best_ord = ord_base + j, best_idx = b * (uint32_t)p.stride + j;
+            while (true) {
+                float best_lb = INF;
+                int nn = -1;
+#pragma unroll
+                for (int ox = 0; ox < 3; ++ox) {
+                    const float ax = ox == 0 ? sxm : (ox == 2 ? sxp : 0.0f);
+                    if (ax > bound) continue;
+#pragma unroll
+                    for (int oy = 0; oy < 3; ++oy) {
+                        const float ay = ax + (oy == 0 ? sym : (oy == 2 ? syp : 0.0f));
+                        if (ay > bound) continue;
+#pragma unroll
+                        for (int oz = 0; oz < 3; ++oz) {
+                            const float az = ay + (oz == 0 ? szm : (oz == 2 ? szp : 0.0f));
+                            const int id = ox * 9 + oy * 3 + oz;
+                            if (az < best_lb && !((visited >> id) & 1u)) best_lb = az, nn = id;
+                        }
                     }
-                    ord_base += c;
+                }
+                if (nn < 0 || !(best_lb <= bound)) break;
+                if (budget-- <= 0) {
+                    heavy = true;
+                    break;
+                }
+                visited |= 1u << nn;
+                const int ox = nn / 9 - 1, oy = (nn / 3) % 3 - 1, oz = nn % 3 - 1;
+                const int nx = kx + ox, ny = ky + oy, nz = kz + oz;
+                uint32_t nblk = 0, ncnt = 0;
+                if (COUNT) n_probes += 1;
+                if (key_in_range(nx, ny, nz) && tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), nblk, ncnt) && ncnt > 0) {
+                    scan_voxel_thread(p.blk_hot, nblk * (uint32_t)p.stride, ncnt, bx - (float)ox * vs32, by - (float)oy * vs32,
+                                      bz - (float)oz * vs32, qlf, th32, min1, min2, idx1, odd);
+                    if (COUNT) n_scanned += ncnt;
+                    bound = prune_bound(p, min1);
                 }
             }
-            if (STATS && gl == 0) cand += ord_base;
-            // group arg-min on (metric, enumeration order): strict '<' => first minimum wins (core/VoxelHashMap.cpp:89)
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(best);
-            const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
-            const uint32_t mhi = __reduce_min_sync(gmask, hi);
-            const uint32_t mlo = __reduce_min_sync(gmask, hi == mhi ? lo : 0xffffffffu);
-            const bool tie = (hi == mhi) && (lo == mlo);
-            const uint32_t mord = __reduce_min_sync(gmask, tie ? best_ord : 0xffffffffu);
-            bool accept = false;
-            double4 nb = make_double4(0, 0, 0, 0);
-            if (mord != 0xffffffffu) {
-                const unsigned wm = __ballot_sync(gmask, tie && best_ord == mord) & gmask;
-                const uint32_t widx = __shfl_sync(gmask, best_idx, __ffs(wm) - 1);
-                nb = ldg256(p.blk_pts + widx);
-                const double dx = __dsub_rn(nb.x, cx), dy = __dsub_rn(nb.y, cy), dz = __dsub_rn(nb.z, cz);
-                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                accept = __dsqrt_rn(d2) < p.max_dist;  // core/VoxelHashMap.cpp:111
+            // ---- decide: unique within the error band => idx1 IS the f64 arg-min ----
+            if (!heavy && !odd && min1 < INF) {
+                if (min2 > band_limit(p, min1))
+                    widx = idx1;
+                else
+                    odd = true;
             }
-            if (gl == i) tx = nb.x, ty = nb.y, tz = nb.z, tl = nb.w, ok = accept;
         }
 
-        if (ok) {
-            // residual, Geman-McClure weight and the 16 sums (core/Registration.cpp:62-70,79-85)
-            const double rx = sx - tx, ry = sy - ty, rz = sz - tz;
-            const double r2 = (rx * rx + ry * ry) + rz * rz;
-            const double den = p.kern + r2;
-            const double w = (p.kern * p.kern) / (den * den);
-            const double wx = w * sx, wy = w * sy, wz = w * sz;
-            acc[0] += w;
-            acc[1] += wx, acc[2] += wy, acc[3] += wz;
-            acc[4] += wx * sx, acc[5] += wy * sy, acc[6] += wz * sz;
-            acc[7] += wx * sy, acc[8] += wx * sz, acc[9] += wy * sz;
-            acc[10] += w * rx, acc[11] += w * ry, acc[12] += w * rz;
-            acc[13] += w * (sy * rz - sz * ry), acc[14] += w * (sz * rx - sx * rz), acc[15] += w * (sx * ry - sy * rx);
-            npairs += 1.0;
+        SAGE_STAMP(7);
+        // ---- queries whose f32 ranking was ambiguous: the whole warp re-ranks them in f64, one at a time ----
+        unsigned em = __ballot_sync(0xffffffffu, valid && odd && !heavy);
+        while (em) {
+            const int l = __ffs(em) - 1;
+            em &= em - 1;
+            const double4 c = ld256(p.src + wbase + l);
+            const uint32_t w = nn_exact<32>(p, 0xffffffffu, lane, c.x, c.y, c.z, c.w, trunc_div(c.x, vs), trunc_div(c.y, vs),
+                                            trunc_div(c.z, vs));
+            if (lane == l) widx = w;
+            if (COUNT && lane == 0) n_exact += 1;
         }
-        if (p.tgt_out && valid) {
-            st256(p.tgt_out + q, make_double4(tx, ty, tz, tl));
-            p.matched_out[q] = ok ? 1 : 0;
+
+        SAGE_STAMP(8);
+        // ---- acceptance, residual, weight and the sums ----
+        {
+            double4 nb = make_double4(0, 0, 0, 0);
+            bool ok = false;
+            if (widx != kNil) {
+                const double4 s = ld256(p.src + q);  // this thread's own (transformed) point again: cheaper than 8 live registers
+                nb = ldg256(p.blk_pts + widx);
+                ok = accept_pair(nb, s.x, s.y, s.z, p.max_dist);
+                if (ok) accumulate_pair(s_acc, threadIdx.x, p.kern, s.x, s.y, s.z, nb.x, nb.y, nb.z);
+            }
+            if (p.tgt_out && valid && !heavy) {
+                st256(p.tgt_out + q, nb);
+                p.matched_out[q] = ok ? 1 : 0;
+            }
         }
+
+        SAGE_STAMP(9);
+        // ---- deferred queries of this pass: deterministic compaction (warp order, lane order), then one warp per query ----
+        const unsigned hm = __ballot_sync(0xffffffffu, heavy);
+        if (lane == 0) s_cnt[warp] = __popc(hm);
+        if (p.dbg && threadIdx.x == 0 && pass == 0) p.dbg[kDbg * blockIdx.x + 1] = gtime();  // warp 0 done with its light phase
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            before += w < warp ? s_cnt[w] : 0u;
+            total += s_cnt[w];
+        }
+        if (heavy) s_list[before + __popc(hm & ((1u << lane) - 1u))] = q;
+        __syncthreads();
+        if (p.dbg && threadIdx.x == 0 && pass == 0) p.dbg[kDbg * blockIdx.x + 2] = gtime();  // whole block done with the light phase
+        for (uint32_t i = warp; i < total; i += kWarps) {
+            const uint32_t hq = s_list[i];
+            const double4 s = ld256(p.src + hq);  // transformed above (same block, ordered by the barrier)
+            const uint32_t w = search_query_warp<COUNT>(p, lane, s, n_scanned, n_probes, n_exact);
+            if (lane == 0) {
+                double4 nb = make_double4(0, 0, 0, 0);
+                bool ok = false;
+                if (w != kNil) {
+                    nb = ldg256(p.blk_pts + w);
+                    ok = accept_pair(nb, s.x, s.y, s.z, p.max_dist);
+                    if (ok) accumulate_pair(s_acc, threadIdx.x, p.kern, s.x, s.y, s.z, nb.x, nb.y, nb.z);
+                }
+                if (p.tgt_out) {
+                    st256(p.tgt_out + hq, nb);
+                    p.matched_out[hq] = ok ? 1 : 0;
+                }
+                if (COUNT) n_heavy += 1;
+            }
+        }
+        if (pass + 1 < passes) __syncthreads();  // s_cnt / s_list are reused by the next pass
     }
 
-    // deterministic reduction: lanes (butterfly) -> warps (fixed order) -> blocks (fixed order, last block)
-    const int warp = threadIdx.x >> 5;
+    // per-block partial sums: threads (fixed tree per sum) -> blocks (fixed order, by the last block to finish)
+    __syncthreads();
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x + 3] = gtime();
+    for (int k = warp; k < kSums; k += kWarps) {
+        double v = 0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        double v = acc[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][k] = v;
-    }
-    {
-        double v = npairs;
+        for (int t = 0; t < kWarps; ++t) v += s_acc[k][lane + 32 * t];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][16] = v;
+        if (lane == 0) {
+            p.partials[(size_t)k * gridDim.x + blockIdx.x] = v;  // [sum][block]
+            __threadfence();
+        }
     }
-    if (STATS) {
+    if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            occ += __shfl_xor_sync(0xffffffffu, occ, o);
-            cand += __shfl_xor_sync(0xffffffffu, cand, o);
+            n_scanned += __shfl_xor_sync(0xffffffffu, n_scanned, o);
+            n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
+            n_exact += __shfl_xor_sync(0xffffffffu, n_exact, o);
+            n_heavy += __shfl_xor_sync(0xffffffffu, n_heavy, o);
         }
         if (lane == 0) {
-            atomicAdd(&st->stat_occupied, occ);
-            atomicAdd(&st->stat_candidates, cand);
+            atomicAdd(&st->stat_scanned, n_scanned);
+            atomicAdd(&st->stat_probes, n_probes);
+            atomicAdd(&st->stat_exact, n_exact);
+            atomicAdd(&st->stat_heavy, n_heavy);
         }
-    }
-    __syncthreads();
-    if (threadIdx.x < kSums) {
-        double v = 0;
-        for (int wv = 0; wv < kNnThreads / 32; ++wv) v += s_red[wv][threadIdx.x];
-        p.partials[(size_t)blockIdx.x * kSums + threadIdx.x] = v;
-        __threadfence();
     }
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < kSums) {
-        double v = 0;
-        const volatile double *part = p.partials;
-        for (uint32_t b = 0; b < gridDim.x; ++b) v += part[(size_t)b * kSums + threadIdx.x];
-        st->sums[threadIdx.x] = v;
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x] = gtime();
+    // the last block adds the per-block partials: warp w owns sums w, w+8, w+16 (three independent chains); lane l adds
+    // blocks l, l+32, ... in order, then a fixed butterfly — the same tree for a given grid, so results are reproducible
+    {
+        const double *p0 = p.partials + (size_t)warp * gridDim.x, *p1 = p0 + (size_t)kWarps * gridDim.x, *p2 = p1 + (size_t)kWarps * gridDim.x;
+        const bool has2 = warp + 2 * kWarps < kSums;
+        double v0 = 0, v1 = 0, v2 = 0;
+#pragma unroll 4
+        for (uint32_t b = lane; b < gridDim.x; b += 32) {
+            v0 += __ldcg(p0 + b);
+            v1 += __ldcg(p1 + b);
+            if (has2) v2 += __ldcg(p2 + b);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        }
+        if (lane == 0) {
+            st->sums[warp] = v0, st->sums[warp + kWarps] = v1;
+            if (has2) st->sums[warp + 2 * kWarps] = v2;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         st->ticket = 0;
+        if (p.dbg) p.dbg[kDbg * gridDim.x + 1] = gtime();
         if (p.solve) icp_solve_step(st);
+        if (p.dbg) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
+    }
+}
+
+// Neighbourhood statistics for the algorithmic-bytes figure: per query, how many of the 27 voxels exist
+// and how many points they hold.  One thread per (query, voxel).
+__global__ void nn_stats_kernel(const TblEntry *tbl, uint32_t mask, const double4 *src, uint32_t n, double vs, IcpState *st) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = t / 32, pr = t % 32;
+    unsigned long long occ = 0, cand = 0;
+    if (q < n && pr < 27) {
+        const double4 s = src[q];
+        const int nx = trunc_div(s.x, vs) + (int)pr / 9 - 1, ny = trunc_div(s.y, vs) + ((int)pr / 3) % 3 - 1, nz = trunc_div(s.z, vs) + (int)pr % 3 - 1;
+        uint32_t b, c;
+        if (key_in_range(nx, ny, nz) && tbl_find(tbl, mask, pack_key(nx, ny, nz), b, c)) occ = 1, cand = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        occ += __shfl_xor_sync(0xffffffffu, occ, o);
+        cand += __shfl_xor_sync(0xffffffffu, cand, o);
+    }
+    if ((threadIdx.x & 31) == 0 && occ) {
+        atomicAdd(&st->stat_occupied, occ);
+        atomicAdd(&st->stat_candidates, cand);
     }
 }
 
@@ -311,31 +664,41 @@ void VoxelMapGPU::profile_read(long long *launches, double *ms) {
 }
 
 // mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
-// as given; mode 2: statistics pass.
+// as given; mode 2: as mode 1 with the search-work counters on.
 void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode,
                                    double4 *tgt_out, uint8_t *matched_out) {
     if (nn_grid_ == 0) {
         int per_sm = 0;
-        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_normal_eq_kernel<32, false>, kNnThreads, 0));
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_search_kernel<false>, kNnThreads, 0));
         nn_grid_ = sm_count_ * (per_sm > 0 ? per_sm : 1);
-        partials_.ensure((size_t)nn_grid_ * kSums);
+        partials_.ensure((size_t)kSums * nn_grid_);
+        if (const char *e = getenv("SAGE_LIGHT_PROBES")) light_probes_ = atoi(e);  // tuning knob
     }
-    constexpr int G = 32;
-    const uint32_t groups_max = (uint32_t)nn_grid_ * (kNnThreads / G);
-    // queries per group per pass: Q = 1 keeps every SM busy for small scans; for big scans split the queries evenly
-    // over the fewest passes so that no group runs an extra, mostly empty pass
-    const uint32_t passes = (uint32_t)((n + (size_t)groups_max * G - 1) / ((size_t)groups_max * G));
-    uint32_t Q = (uint32_t)((n + (size_t)groups_max * passes - 1) / ((size_t)groups_max * (passes ? passes : 1)));
-    Q = Q < 1 ? 1 : (Q > (uint32_t)G ? (uint32_t)G : Q);
-    const uint32_t groups_needed = (uint32_t)((n + Q - 1) / Q);
-    uint32_t grid = (groups_needed + (kNnThreads / G) - 1) / (kNnThreads / G);
+    // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
+    // there is a chunk for every block, fewer blocks for small scans
+    uint32_t grid = (uint32_t)((n + 31) / 32);
     grid = grid < 1 ? 1 : (grid > (uint32_t)nn_grid_ ? (uint32_t)nn_grid_ : grid);
 
     IterParams p;
-    p.tbl = tbl_.p, p.mask = tbl_cap_ - 1, p.blk_pts = blk_pts_.p, p.stride = stride_, p.voxel_size = voxel_size_;
-    p.src = src, p.n = (uint32_t)n, p.chunk = Q;
+    p.tbl = tbl_.p, p.mask = tbl_cap_ - 1, p.blk_pts = blk_pts_.p, p.blk_hot = blk_hot_.p, p.stride = stride_, p.voxel_size = voxel_size_;
+    p.src = src, p.n = (uint32_t)n;
     p.max_dist = max_dist, p.kern = kernel, p.sem_th = sem_th;
+    // f32 error model (derivation in DESIGN.md §4): per-axis error of (record - query) <= 8 u vs, u = 2^-24, so
+    // |D32 - D| <= 28 u vs sqrt(D) + 3.1 u D and the metric (D or D * th) adds 2.1 u relative; constants doubled.
+    {
+        const double u = 5.9604644775390625e-8, vsd = voxel_size_;
+        const bool ok = sem_th > 0.0 && sem_th < 1e30 && vsd > 1e-6 && vsd < 1e6;
+        const double smin = ok ? (sem_th < 1.0 ? sem_th : 1.0) : 1.0, smax = ok ? (sem_th > 1.0 ? sem_th : 1.0) : 1.0;
+        p.fast_ok = ok ? 1 : 0;
+        p.vs32 = (float)vsd, p.th32 = (float)sem_th;
+        p.smin32 = (float)(smin * (1.0 - 1e-5)), p.inv_smin32 = (float)((1.0 + 1e-5) / smin);
+        p.err_scale = (float)(smax * (1.0 + 1e-5));
+        p.err_a = (float)(64.0 * u * vsd), p.err_b = (float)(12.0 * u), p.err_c = (float)(1e-11 * vsd * vsd);
+        p.box_margin = (float)(32.0 * u * vsd);
+    }
     p.st = icp_.p, p.partials = partials_.p, p.tgt_out = tgt_out, p.matched_out = matched_out;
+    p.dbg = (mode == 0 && dbg_on_) ? dbg_.p : nullptr;
+    p.light_probes = light_probes_;
     p.apply_est = (mode == 0), p.respect_done = (mode == 0);
     p.solve = (mode == 0 && comm_ == nullptr);
 
@@ -350,9 +713,9 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].first, stream_));
     }
     if (mode == 2)
-        SAGE_LAUNCH((nn_normal_eq_kernel<G, true>), grid, kNnThreads, 0, stream_, p);
+        SAGE_LAUNCH(nn_search_kernel<true>, grid, kNnThreads, 0, stream_, p);
     else
-        SAGE_LAUNCH((nn_normal_eq_kernel<G, false>), grid, kNnThreads, 0, stream_, p);
+        SAGE_LAUNCH(nn_search_kernel<false>, grid, kNnThreads, 0, stream_, p);
     if (prof) {
         SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].second, stream_));
         ++prof_used_;
@@ -455,11 +818,38 @@ void VoxelMapGPU::nn_stats(const double *xyzl, size_t n, unsigned long long *occ
     icp_.ensure(1);
     icp_pin_.ensure(1);
     SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, pose_identity(), 1, 0.0);
-    launch_iteration(d, n, 0.0, 1.0, 1.0, 2, nullptr, nullptr);
+    SAGE_LAUNCH(nn_stats_kernel, (unsigned)((n * 32 + 255) / 256), 256, 0, stream_, tbl_.p, tbl_cap_ - 1, d, (uint32_t)n, voxel_size_, icp_.p);
     SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
     SAGE_CUDA(cudaStreamSynchronize(stream_));
     *occupied = icp_pin_.p->stat_occupied;
     *candidates = icp_pin_.p->stat_candidates;
+}
+
+// development aid: per-block globaltimer stamps of the LAST profiled iteration (4 per block + 4 trailing)
+size_t VoxelMapGPU::debug_timeline(unsigned long long *out, size_t cap) {
+    set_device();
+    dbg_on_ = true;
+    dbg_.ensure((size_t)kDbg * 4096 + 8);
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    const size_t n = (size_t)kDbg * (nn_grid_ > 0 ? nn_grid_ : 1) + 4;
+    if (out && cap >= n) SAGE_CUDA(cudaMemcpy(out, dbg_.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return n;
+}
+
+void VoxelMapGPU::search_work(const double *xyzl, size_t n, double max_dist, double sem_th, unsigned long long *scanned,
+                              unsigned long long *probes, unsigned long long *exact, unsigned long long *heavy) {
+    set_device();
+    *scanned = *probes = *exact = 0;
+    if (n == 0 || empty()) return;
+    double4 *d = stage_points(xyzl, n);
+    icp_.ensure(1);
+    icp_pin_.ensure(1);
+    SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, pose_identity(), 1, 0.0);
+    launch_iteration(d, n, max_dist, 1.0, sem_th, 2, nullptr, nullptr);
+    SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    *scanned = icp_pin_.p->stat_scanned, *probes = icp_pin_.p->stat_probes, *exact = icp_pin_.p->stat_exact;
+    if (heavy) *heavy = icp_pin_.p->stat_heavy;
 }
 
 }  // namespace sage

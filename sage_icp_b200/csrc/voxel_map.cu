@@ -126,8 +126,10 @@ __global__ void map_link_kernel(MapView m, const uint32_t *slot, uint32_t *next,
 }
 
 // VoxelBlock::AddPoint — core/VoxelHashMap.hpp:45-70
-__device__ __forceinline__ void add_point_rule(const MapView &m, double4 *vox, int &cnt, const double4 &p) {
+__device__ __forceinline__ void add_point_rule(const MapView &m, double4 *vox, float4 *hot, int kx, int ky, int kz, int &cnt,
+                                               const double4 &p) {
     if (cnt < m.basic || cnt == 0) {  // cnt == 0: a new voxel is created holding its first point whatever the label
+        hot[cnt] = hot_record(p, kx, ky, kz, m.voxel_size);
         vox[cnt++] = p;
         return;
     }
@@ -136,11 +138,13 @@ __device__ __forceinline__ void add_point_rule(const MapView &m, double4 *vox, i
     bool is_basic = false;
     for (int k = 0; k < m.n_basic_labels; ++k) is_basic |= (m.basic_labels[k] == label);
     if (!is_basic && cnt < m.basic + m.critical) {
+        hot[cnt] = hot_record(p, kx, ky, kz, m.voxel_size);
         vox[cnt++] = p;
         return;
     }
     for (int k = 0; k < cnt; ++k)
         if (__double2int_rz(vox[k].w) == 0) {
+            hot[k] = hot_record(p, kx, ky, kz, m.voxel_size);
             vox[k] = p;
             return;
         }
@@ -154,6 +158,9 @@ __global__ void map_replay_kernel(MapView m, const double4 *pts, const uint32_t 
     const uint32_t b = m.tbl[s].block;
     const uint32_t head = m.blk_head[b];
     double4 *vox = m.blk_pts + (size_t)b * m.stride;
+    float4 *hot = m.blk_hot + (size_t)b * m.stride;
+    int kx, ky, kz;
+    unpack_key(m.blk_key[b], kx, ky, kz);
     int cnt = m.blk_cnt[b];
     long long last = -1;
     while (true) {
@@ -161,7 +168,7 @@ __global__ void map_replay_kernel(MapView m, const double4 *pts, const uint32_t 
         for (uint32_t j = head; j != kNil; j = next[j])
             if ((long long)j > last && j < best) best = j;
         if (best == kNil) break;
-        add_point_rule(m, vox, cnt, pts[best]);
+        add_point_rule(m, vox, hot, kx, ky, kz, cnt, pts[best]);
         last = best;
     }
     m.blk_cnt[b] = cnt;
@@ -185,6 +192,18 @@ __global__ void map_evict_kernel(MapView m, double ox, double oy, double oz, dou
         atomicSub(&m.ctrl->n_live, 1u);
         atomicAdd(&m.ctrl->evicted, 1u);
     }
+}
+
+// search records of a bulk-loaded map (load()): one thread per slot
+__global__ void map_build_hot_kernel(MapView m, uint32_t n_blocks) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n_blocks * m.stride) return;
+    const uint32_t b = (uint32_t)(i / m.stride);
+    const int j = (int)(i % m.stride);
+    if (m.blk_key[b] == kEmptyKey || j >= m.blk_cnt[b]) return;
+    int kx, ky, kz;
+    unpack_key(m.blk_key[b], kx, ky, kz);
+    m.blk_hot[i] = hot_record(m.blk_pts[i], kx, ky, kz, m.voxel_size);
 }
 
 __global__ void map_count_points_kernel(MapView m) {
@@ -240,7 +259,7 @@ VoxelMapGPU::~VoxelMapGPU() {
 MapView VoxelMapGPU::view() {
     MapView v;
     v.tbl = tbl_.p, v.mask = tbl_cap_ - 1;
-    v.blk_key = blk_key_.p, v.blk_cnt = blk_cnt_.p, v.blk_head = blk_head_.p, v.blk_slot = blk_slot_.p, v.blk_pts = blk_pts_.p;
+    v.blk_key = blk_key_.p, v.blk_cnt = blk_cnt_.p, v.blk_head = blk_head_.p, v.blk_slot = blk_slot_.p, v.blk_pts = blk_pts_.p, v.blk_hot = blk_hot_.p;
     v.free_list = free_list_.p, v.ctrl = ctrl_.p;
     v.stride = stride_, v.basic = basic_, v.critical = critical_;
     v.n_basic_labels = (int)basic_labels_.size();
@@ -317,8 +336,9 @@ void VoxelMapGPU::reserve(size_t extra) {
         blk_slot_.ensure(want, stream_, true);
         free_list_.ensure(want, stream_, true);
         blk_pts_.ensure(want * (size_t)stride_, stream_, true);
+        blk_hot_.ensure(want * (size_t)stride_, stream_, true);
         blk_cap_ = (uint32_t)std::min<size_t>({blk_key_.cap, blk_cnt_.cap, blk_head_.cap, blk_slot_.cap, free_list_.cap,
-                                                blk_pts_.cap / (size_t)stride_});
+                                                blk_pts_.cap / (size_t)stride_, blk_hot_.cap / (size_t)stride_});
     }
     if (2 * (live_bound_ + extra) > tbl_cap_) {
         uint32_t cap = tbl_cap_;
@@ -430,6 +450,7 @@ void VoxelMapGPU::load(const int32_t *keys, const int32_t *counts, const double 
     SAGE_CUDA(cudaMemsetAsync(blk_head_.p, 0xff, n_voxels * sizeof(uint32_t), stream_));
     SAGE_LAUNCH(ctrl_set_kernel, 1, 1, 0, stream_, ctrl_.p, (uint32_t)n_voxels, (uint32_t)n_voxels);
     hi_bound_ = live_bound_ = n_voxels;
+    SAGE_LAUNCH(map_build_hot_kernel, blocks_for(n_voxels * (size_t)stride_), kThreads, 0, stream_, view(), (uint32_t)n_voxels);
     rebuild_table(tbl_cap_);
     SAGE_CUDA(cudaStreamSynchronize(stream_));
 }

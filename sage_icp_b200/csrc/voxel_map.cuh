@@ -18,7 +18,8 @@ struct MapView {
     int32_t *blk_cnt;
     uint32_t *blk_head;  // per-block arrival list head (kNil between updates)
     uint32_t *blk_slot;  // table slot of the block
-    double4 *blk_pts;    // [block][stride] x, y, z, label — bit-identical to Eigen::Vector4d
+    double4 *blk_pts;    // [block][stride] x, y, z, label — bit-identical to Eigen::Vector4d ("cold" exact copy)
+    float4 *blk_hot;     // [block][stride] 16-byte search record: f32 offsets from the voxel origin + label (see hot_record)
     uint32_t *free_list;
     MapCtrl *ctrl;
     int stride;  // basic + critical
@@ -60,9 +61,13 @@ public:
     void normal_equations(const double *xyzl, size_t n, double max_dist, double kernel, double sem_th, double JTJ[36], double JTr[6],
                           long long *pairs);
     void nn_stats(const double *xyzl, size_t n, unsigned long long *occupied, unsigned long long *candidates);
+    // work the search kernel actually does on these queries: records scanned, table probes, queries re-ranked in f64
+    void search_work(const double *xyzl, size_t n, double max_dist, double sem_th, unsigned long long *scanned,
+                     unsigned long long *probes, unsigned long long *exact, unsigned long long *heavy = nullptr);
 
     cudaStream_t stream() const { return stream_; }
     int device() const { return device_; }
+    size_t debug_timeline(unsigned long long *out, size_t cap);
     void profile_enable(bool on);
     void profile_read(long long *launches, double *ms);
 
@@ -99,6 +104,7 @@ private:
     DevBuf<int32_t> blk_cnt_;
     DevBuf<uint32_t> blk_head_, blk_slot_, free_list_;
     DevBuf<double4> blk_pts_;
+    DevBuf<float4> blk_hot_;
     uint32_t blk_cap_ = 0;
     DevBuf<MapCtrl> ctrl_;
     PinBuf<MapCtrl> ctrl_pin_;
@@ -116,6 +122,9 @@ private:
     PinBuf<IcpState> icp_pin_;
     DevBuf<double> partials_;
     int nn_grid_ = 0;
+    int light_probes_ = 8;  // neighbour probes per query in the thread-per-query phase before the query is deferred
+    bool dbg_on_ = false;
+    DevBuf<unsigned long long> dbg_;
 
     // profiling
     bool profile_ = false;

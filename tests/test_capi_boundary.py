@@ -1,0 +1,118 @@
+"""The drop-in boundary without a GPU: the C-ABI library loads, exports every symbol include/sage_icp_b200.h declares,
+fails loudly (no CPU fallback) when no sm_100 device is present, and its pure-host entry points work."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import sage_icp_b200 as sg
+    sg.build_library()
+    return sg.load_library()
+
+
+def test_header_is_plain_c():
+    """No C++ / torch types in the signatures: the header compiles as C99."""
+    src = '#include "sage_icp_b200.h"\nint main(void) { return sage_device_count() < 0; }\n'
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                       input=src.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from sage_icp_b200.capi import declared_symbols
+    syms = declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    out = subprocess.run(["nm", "-D", "--defined-only", lib._name], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (sage_[a-z0-9_]+)", out))
+    assert set(syms) <= exported
+    # the library is self-contained CUDA + C++: it must not pull in torch or the oracle
+    needed = subprocess.run(["ldd", lib._name], capture_output=True, text=True).stdout
+    assert "torch" not in needed and "oracle" not in needed
+
+
+def test_sm100a_code_is_in_the_library(lib):
+    out = subprocess.run(["cuobjdump", "-lelf", lib._name], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def _has_gpu():
+    import sage_icp_b200 as sg
+    return sg.device_count() > 0
+
+
+def test_no_device_means_loud_failure(lib, cfg):
+    """The product path has no CPU fallback: on a box without a B200 every create call fails with a message."""
+    if _has_gpu():
+        pytest.skip("a B200 is visible here")
+    import sage_icp_b200 as sg
+    assert sg.device_count() == 0
+    with pytest.raises(sg.SageError, match="(?i)device|cuda"):
+        sg.SageMap(0.8, 100.0, 20, 20, [40])
+    with pytest.raises(sg.SageError, match="(?i)device|cuda"):
+        sg.SagePipeline(cfg)
+
+
+def test_package_does_not_import_the_oracle():
+    code = "import sys, sage_icp_b200, sage_icp_b200.capi, sage_icp_b200.synthetic; print(any(m.startswith('oracle') for m in sys.modules))"
+    out = subprocess.run(["python", "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.stdout.strip() == "False", out.stdout + out.stderr
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sage_icp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle_py" not in txt and "liboracle" not in txt and '#include "../../oracle' not in txt, f
+
+
+def test_shard_range_partitions_exactly(lib):
+    import sage_icp_b200 as sg
+    for n in (0, 1, 7, 120000, 500000, 2 ** 33 + 5):
+        for world in (1, 2, 3, 4, 8):
+            edges = [sg.shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            sizes = [e - b for b, e in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(sg.SageError):
+        sg.shard_range(10, 2, 2)
+
+
+def test_transform_to_last_frame_host_entry_point(lib, orc):
+    """sageICP::TransformToLastFrame (pipeline/sageICP.cpp:123-129) is pure host arithmetic: callable without a device."""
+    rng = np.random.default_rng(0)
+    pts = np.c_[rng.normal(0, 10, (50, 3)), rng.choice([40.0, 0.0], 50)]
+    a, b = orc.se3_exp(rng.normal(size=6) * 0.3), orc.se3_exp(rng.normal(size=6) * 0.3)
+    out = np.empty_like(pts)
+    dp = C.POINTER(C.c_double)
+    rc = lib.sage_transform_to_last_frame(None, a.ctypes.data_as(dp), b.ctypes.data_as(dp), pts.ctypes.data_as(dp), C.c_size_t(50),
+                                          out.ctypes.data_as(dp))
+    assert rc == 0
+    T = orc.se3_mul(orc.se3_inverse(a), b)
+    exp = np.array([orc.se3_act(T, p[:3]) for p in pts])
+    assert np.allclose(out[:, :3], exp, atol=1e-12) and np.array_equal(out[:, 3], pts[:, 3])
+
+
+def test_config_pod_layout_matches_the_header(cfg):
+    """ctypes mirror == C struct: compile a probe that prints sizeof/offsetof and compare."""
+    from sage_icp_b200.config import ConfigPOD
+    fields = [f[0] for f in ConfigPOD._fields_]
+    body = "".join(f'printf("{f} %zu\\n", offsetof(sage_config_pod, {f}));' for f in fields)
+    src = f'#include <stdio.h>\n#include <stddef.h>\n#include "sage_icp_b200.h"\nint main(void){{ printf("size %zu\\n", sizeof(sage_config_pod)); {body} return 0; }}'
+    exe = "/tmp/sage_pod_probe"
+    r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-x", "c", "-", "-o", exe], input=src.encode(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    out = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines())
+    assert int(out["size"]) == C.sizeof(ConfigPOD)
+    for f in fields:
+        assert int(out[f]) == getattr(ConfigPOD, f).offset, f
+    pod = cfg.to_pod()
+    assert pod.n_groups == len(cfg.voxel_labels) == 6 and pod.voxel_size_map == 0.8 and pod.sem_th == 0.4

@@ -70,45 +70,56 @@ def algorithmic_bytes(n_q: int, occupied: int, candidates: int) -> float:
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region: NVML from a thread every 5 ms (the timed region is tens
+    of milliseconds, far too short for `nvidia-smi -lms`)."""
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.sm, self.reasons, self.max_mhz, self.stop_flag = [], set(), None, False
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(device)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # NVML indexes physical devices: honour CUDA_VISIBLE_DEVICES when it lists plain ordinals
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device])
+                except (ValueError, IndexError):
+                    idx = device
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.BAD.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self.nv is None:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
-        os.unlink(self.f.name)
-        sm, reasons = [], set()
-        for r in rows:
-            if len(r) < 9:
-                continue
-            try:
-                sm.append(float(r[1])); out["sm_max_mhz"] = float(r[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
-            out["sm_mhz"] = float(np.median(busy))
-        out["reasons"] = sorted(reasons)
-        out["samples"] = len(sm)
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+        out["reasons"] = sorted(self.reasons)
+        out["samples"] = len(self.sm)
         return out
 
 
@@ -164,7 +175,7 @@ def workload_config(args, map_points, map_voxels):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--map-points", type=int, default=5_000_000)
@@ -265,7 +276,7 @@ def main():
         step_resident(s)
     n_kernels, kernel_ms = gmap.profile_read()
     gmap.profile_enable(False)
-    alg = []
+    alg, work = [], np.zeros(4)
     for s in range(args.warmup, total):
         q = shards_dev[s].cpu().numpy().copy()
         # statistics at the positions the first iteration sees (guess applied), counted exactly on the device map
@@ -278,6 +289,9 @@ def main():
         qq[:, 2] = q[:, 2] + g[2]
         occ, cand = gmap.nn_stats(qq)
         alg.append(algorithmic_bytes(len(qq), occ, cand))
+        if s < args.warmup + 4:  # what the kernel really touches (first-iteration positions), a few steps are enough
+            work += np.array(gmap.search_work(qq, MAX_DIST, SEM_TH)) / len(qq)
+            n_work = s - args.warmup + 1
     bytes_per_launch = float(np.mean(alg))
     peak, peak_src = measured_peak_gbs()
     achieved = bytes_per_launch * n_kernels / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
@@ -324,10 +338,15 @@ def main():
                 "d2h_bytes_per_step": 7 * 8 + 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "nn_normal_eq_kernel (correspondence search + normal equations, 1 launch per GN iteration)",
+        "roofline": {"bound": "hbm", "kernel": "nn_search_kernel (correspondence search + normal equations + GN step, 1 launch per iteration)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": int(n_kernels),
-                     "avg_launch_us": 1e3 * kernel_ms / max(1, n_kernels)},
+                     "avg_launch_us": 1e3 * kernel_ms / max(1, n_kernels),
+                     "note": "achieved = algorithmic bytes of the reference's 27-voxel scan (SURVEY.md 8d) / measured kernel time; the kernel "
+                             "prunes voxels that provably cannot hold the arg-min, so it requests fewer bytes than that (kernel_work)",
+                     "kernel_work_per_query": {"records_scanned": work[0] / n_work, "table_probes": work[1] / n_work,
+                                               "f64_reranked": work[2] / n_work, "deferred_to_warp_phase": work[3] / n_work,
+                                               "requested_bytes": 16 * (work[0] + work[1]) / n_work + 32 + 32 + 32}},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -53,6 +53,7 @@ struct IterParams {
     int apply_est;
     int solve;
     int respect_done;
+    int all_warp;      // 1: warp-per-query for every query (small scans)
     int light_probes;  // neighbour probes a query may spend in the thread-per-query phase before it is deferred
     unsigned long long *dbg;  // optional per-block timeline (tools/perf_probe.py): 4 globaltimer stamps per block + 4 global
 };
@@ -92,30 +93,45 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 __device__ __forceinline__ double shfl_d(unsigned mask, double v, int lane) { return __shfl_sync(mask, v, lane); }
 
-// One Gauss-Newton step from the reduced sums: x = LDLT(JTJ)^-1 (-JTr); est = exp(x); T_icp = est * T_icp;
-// stop when |log(est)| < threshold (core/Registration.cpp:92-93,133-137).
-__device__ __noinline__ void icp_solve_step(IcpState *st) {
-    const double *S = st->sums;
+// One Gauss-Newton step from the reduced sums: x = LDLT(JTJ)^-1 (-JTr); est = exp(x); T_icp = est * T_icp; stop when
+// |log(est)| < threshold (core/Registration.cpp:92-93,133-137).  Called by EVERY thread of a block of >= 64 threads (it
+// synchronises): thread 0 solves and exponentiates, then thread 0 (pose products) and thread 32 (log norm) run side by side.
+__device__ __noinline__ void icp_solve_xi(const double *S, double xi[6]) {
     // JTJ = sum w [[I, -s^],[s^, |s|^2 I - s s^T]],  JTr = sum w [r; s x r]   
     const double w = S[0], x = S[1], y = S[2], z = S[3], xx = S[4], yy = S[5], zz = S[6], xy = S[7], xz = S[8], yz = S[9];
     double A[6][6] = {{w, 0, 0, 0, z, -y},       {0, w, 0, -z, 0, x},        {0, 0, w, y, -x, 0},
                       {0, -z, y, yy + zz, -xy, -xz}, {z, 0, -x, -xy, xx + zz, -yz}, {-y, x, 0, -xz, -yz, xx + yy}};
-    double b[6], xi[6];
+    double b[6];
+#pragma unroll
     for (int i = 0; i < 6; ++i) b[i] = -S[10 + i];
-    solve6_ldlt(A, b, xi);
-    const Pose est = pose_exp(xi);
-    st->est = est;
-    st->T_icp = pose_mul(est, st->T_icp);
-    st->iter += 1;
-    double lg[6];
-    pose_log(est, lg);
-    double n2 = 0;
-    for (int i = 0; i < 6; ++i) n2 += lg[i] * lg[i];
-    const double nrm = sqrt(n2);
-    st->last_norm = nrm;
-    if (nrm < st->est_th || st->iter >= st->max_iters) {
-        st->done = 1;
-        st->result = pose_mul(st->T_icp, st->guess);
+    solve6_ldlt_static(A, b, xi);
+}
+__device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, double *s_norm) {
+    if (threadIdx.x == 0) {
+        double xi[6];
+        icp_solve_xi(st->sums, xi);
+        *s_pose = pose_exp(xi);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const Pose est = *s_pose;
+        st->est = est;
+        const Pose T = pose_mul(est, st->T_icp);
+        st->T_icp = T;
+        st->result = pose_mul(T, st->guess);  // only read once done
+        st->iter += 1;
+    } else if (threadIdx.x == 32) {
+        double lg[6];
+        pose_log(*s_pose, lg);
+        double n2 = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) n2 += lg[i] * lg[i];
+        *s_norm = sqrt(n2);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->last_norm = *s_norm;
+        if (*s_norm < st->est_th || st->iter >= st->max_iters) st->done = 1;
     }
 }
 
@@ -135,9 +151,11 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = 0;
 }
 
-__global__ void icp_solve_kernel(IcpState *st) {
+__global__ void icp_solve_kernel(IcpState *st) {  // <<<1, 64>>>, after the NCCL all-reduce of the sums
+    __shared__ Pose s_pose;
+    __shared__ double s_norm;
     if (st->done) return;
-    icp_solve_step(st);
+    icp_step_block(st, &s_pose, &s_norm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,6 +390,7 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
     __shared__ Pose s_est;
     __shared__ uint32_t s_cnt[kWarps];
     __shared__ uint32_t s_list[kNnThreads];
+    __shared__ double s_norm;
     __shared__ int s_last;
     IcpState *st = p.st;
     if (p.respect_done && st->done) return;
@@ -387,7 +406,35 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
     const float INF = __int_as_float(0x7f800000);
     unsigned long long n_scanned = 0, n_probes = 0, n_exact = 0, n_heavy = 0;
 
-    const uint32_t n_chunks = (p.n + 31) / 32, chunks_per_pass = gridDim.x * kWarps;
+    if (p.all_warp) {
+        // small scans (pipeline level: a few thousand queries): give every query a whole warp straight away
+        for (uint32_t q = blockIdx.x * kWarps + warp; q < p.n; q += gridDim.x * kWarps) {
+            double4 s = ld256(p.src + q);
+            if (p.apply_est) {  // source <- est * source, in place (core/Registration.cpp:133); every lane computes the same
+                const Pose est = s_est;
+                double x, y, z;
+                pose_act(est, s.x, s.y, s.z, x, y, z);
+                s.x = x, s.y = y, s.z = z;
+                if (lane == 0) st256(p.src + q, s);
+            }
+            const uint32_t w = search_query_warp<COUNT>(p, lane, s, n_scanned, n_probes, n_exact);
+            if (lane == 0) {
+                double4 nb = make_double4(0, 0, 0, 0);
+                bool ok = false;
+                if (w != kNil) {
+                    nb = ldg256(p.blk_pts + w);
+                    ok = accept_pair(nb, s.x, s.y, s.z, p.max_dist);
+                    if (ok) accumulate_pair(s_acc, threadIdx.x, p.kern, s.x, s.y, s.z, nb.x, nb.y, nb.z);
+                }
+                if (p.tgt_out) {
+                    st256(p.tgt_out + q, nb);
+                    p.matched_out[q] = ok ? 1 : 0;
+                }
+                if (COUNT) n_heavy += 1;
+            }
+        }
+    }
+    const uint32_t n_chunks = p.all_warp ? 0u : (p.n + 31) / 32, chunks_per_pass = gridDim.x * kWarps;
     const uint32_t passes = (n_chunks + chunks_per_pass - 1) / chunks_per_pass;  // same for every warp of every block
     for (uint32_t pass = 0; pass < passes; ++pass) {
         const uint32_t chunk = (pass * kWarps + warp) * gridDim.x + blockIdx.x;
@@ -613,9 +660,9 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
     if (threadIdx.x == 0) {
         st->ticket = 0;
         if (p.dbg) p.dbg[kDbg * gridDim.x + 1] = gtime();
-        if (p.solve) icp_solve_step(st);
-        if (p.dbg) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
     }
+    if (p.solve) icp_step_block(st, &s_est, &s_norm);
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
 }
 
 // Neighbourhood statistics for the algorithmic-bytes figure: per query, how many of the 27 voxels exist
@@ -676,7 +723,9 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     }
     // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
     // there is a chunk for every block, fewer blocks for small scans
-    uint32_t grid = (uint32_t)((n + 31) / 32);
+    // small scans: one warp per query (all_warp) as long as that is at most two queries per resident warp
+    const bool all_warp = n <= (size_t)nn_grid_ * (kNnThreads / 32) * 2 && !getenv("SAGE_NO_ALL_WARP");
+    uint32_t grid = all_warp ? (uint32_t)((n + kNnThreads / 32 - 1) / (kNnThreads / 32)) : (uint32_t)((n + 31) / 32);
     grid = grid < 1 ? 1 : (grid > (uint32_t)nn_grid_ ? (uint32_t)nn_grid_ : grid);
 
     IterParams p;
@@ -698,7 +747,7 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     }
     p.st = icp_.p, p.partials = partials_.p, p.tgt_out = tgt_out, p.matched_out = matched_out;
     p.dbg = (mode == 0 && dbg_on_) ? dbg_.p : nullptr;
-    p.light_probes = light_probes_;
+    p.light_probes = light_probes_, p.all_warp = all_warp ? 1 : 0;
     p.apply_est = (mode == 0), p.respect_done = (mode == 0);
     p.solve = (mode == 0 && comm_ == nullptr);
 
@@ -722,7 +771,7 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     }
     if (mode == 0 && comm_ != nullptr) {
         nccl_allreduce_sum_f64(comm_, icp_.p->sums, kSums, stream_);
-        SAGE_LAUNCH(icp_solve_kernel, 1, 1, 0, stream_, icp_.p);
+        SAGE_LAUNCH(icp_solve_kernel, 1, 64, 0, stream_, icp_.p);
     }
 }
 

@@ -111,6 +111,21 @@ public:
     Vector4dVectorTuple RegisterFrame(const std::vector<Eigen::Vector4d> &frame, const std::vector<double> &timestamps) {
         return Register(frame, timestamps.size() == frame.size() && !timestamps.empty() ? timestamps.data() : nullptr);
     }
+    // Extension (not in the reference): RegisterFrame straight from a sensor_msgs/PointCloud2 data buffer, i.e.
+    // utils::PointCloud2ToEigen (ros/ros2/Utils.hpp:161-180) + RegisterFrame with the f32 -> f64 widening done on the
+    // device.  In OdometryServer::RegisterFrame (ros/ros2/OdometryServer.cpp:156-167) this replaces the two calls
+    //   const auto points = utils::PointCloud2ToEigen(msg);  odometry_.RegisterFrame(points, timestamps);
+    // by  odometry_.RegisterFramePointCloud2(msg->data.data(), msg->width * msg->height, msg->point_step, 0, 4, 8, 12,
+    //                                        msg->fields.size() == 5 ? 2 : 7, timestamps);
+    Vector4dVectorTuple RegisterFramePointCloud2(const uint8_t *data, size_t n_points, uint32_t point_step, uint32_t x_offset,
+                                                 uint32_t y_offset, uint32_t z_offset, uint32_t label_offset, int label_datatype,
+                                                 const std::vector<double> &timestamps) {
+        double pose[7], t_icp = 0, t_all = 0;
+        Check(sage_register_frame_pointcloud2(Handle(), data, n_points, point_step, x_offset, y_offset, z_offset, label_offset,
+                                              label_datatype, timestamps.size() == n_points && n_points ? timestamps.data() : nullptr,
+                                              pose, &t_icp, &t_all));
+        return {FetchSource(), t_icp, t_all};
+    }
     // pipeline/sageICP.cpp:97-101 — returns {source, frame_downsample}
     Vector4dVectorTuple2 Voxelize(const std::vector<Eigen::Vector4d> &frame) const {
         Vector4dVector source(frame.size()), downsample(frame.size());
@@ -187,10 +202,13 @@ private:
         static_assert(sizeof(Eigen::Vector4d) == 4 * sizeof(double), "Vector4d must be 4 packed doubles");
         double pose[7], t_icp = 0, t_all = 0;
         Check(sage_register_frame(Handle(), Data(frame), frame.size(), timestamps, pose, &t_icp, &t_all));
+        return {FetchSource(), t_icp, t_all};
+    }
+    Vector4dVector FetchSource() {
         const int64_t n = sage_last_source(Handle(), nullptr, 0);
         Vector4dVector source(static_cast<size_t>(n > 0 ? n : 0));
         if (n > 0) sage_last_source(Handle(), Data(source), source.size());
-        return {std::move(source), t_icp, t_all};
+        return source;
     }
 
     sageConfig config_;

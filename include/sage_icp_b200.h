@@ -74,6 +74,15 @@ int sage_reset(sage_pipeline *h);
  * The returned `source` cloud of the reference tuple is fetched with sage_last_source(). */
 int sage_register_frame(sage_pipeline *h, const double *xyzl, size_t n, const double *timestamps, double pose_out[7],
                         double *t_icp, double *t_all);
+/* utils::PointCloud2ToEigen (ros/ros2/Utils.hpp:161-180) fused with RegisterFrame: `data` is the HOST data buffer of a
+ * sensor_msgs/PointCloud2 (width*height = n_points records of point_step bytes; the reference's publishers send packed
+ * 17-byte records f32 x,y,z @0/4/8, u8 label @12, u32 rgb @13 — eval/kitti_pub.py:184-207).  The buffer crosses PCIe as
+ * is and is widened to f64 on the device, exactly as the reference widens it on the host.  label_datatype follows
+ * sensor_msgs/PointField: 2 = UINT8 (messages with 5 fields), 7 = FLOAT32 (the reference's other branch). */
+int sage_register_frame_pointcloud2(sage_pipeline *h, const uint8_t *data, size_t n_points, uint32_t point_step,
+                                    uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, uint32_t label_offset,
+                                    int label_datatype, const double *timestamps, double pose_out[7], double *t_icp,
+                                    double *t_all);
 /* std::get<0>(RegisterFrame(...)) — the double-downsampled query cloud, sensor frame, reference order. */
 int64_t sage_last_source(sage_pipeline *h, double *out, size_t cap_points);
 /* frame_downsample of the last frame (what Update() consumed) — diagnostic, pipeline/sageICP.cpp:68,92 */

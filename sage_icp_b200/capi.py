@@ -273,6 +273,18 @@ class SagePipeline:
                   "sage_register_frame")
         return pose, ti.value, ta.value
 
+    def register_frame_pointcloud2(self, data: np.ndarray, n_points: int, point_step: int, offsets=(0, 4, 8, 12),
+                                   label_datatype: int = 2, timestamps=None):
+        """RegisterFrame on the raw sensor_msgs/PointCloud2 data buffer (uint8 array), unpacked on the device."""
+        data = np.ascontiguousarray(data, dtype=np.uint8); pose = np.empty(7); ti, ta = C.c_double(), C.c_double()
+        assert data.size >= n_points * point_step
+        ts = None if timestamps is None else _d(_c64(timestamps))
+        self._chk(self.L.sage_register_frame_pointcloud2(self.h, data.ctypes.data_as(_u8p), C.c_size_t(n_points), C.c_uint32(point_step),
+                                                         C.c_uint32(offsets[0]), C.c_uint32(offsets[1]), C.c_uint32(offsets[2]),
+                                                         C.c_uint32(offsets[3]), int(label_datatype), ts, _d(pose), C.byref(ti), C.byref(ta)),
+                  "sage_register_frame_pointcloud2")
+        return pose, ti.value, ta.value
+
     def _cloud(self, fn, what):
         n = self._chk(fn(self.h, None, C.c_size_t(0)), what)
         out = np.empty((n, 4))

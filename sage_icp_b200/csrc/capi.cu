@@ -102,6 +102,22 @@ int sage_register_frame(sage_pipeline *h, const double *xyzl, size_t n, const do
         return 0;
     });
 }
+int sage_register_frame_pointcloud2(sage_pipeline *h, const uint8_t *data, size_t n_points, uint32_t point_step, uint32_t x_offset,
+                                    uint32_t y_offset, uint32_t z_offset, uint32_t label_offset, int label_datatype, const double *timestamps,
+                                    double pose_out[7], double *t_icp, double *t_all) {
+    return (int)guarded([&] {
+        if (!h || (!data && n_points)) throw ArgError("null argument");
+        if (label_datatype != 2 && label_datatype != 7) throw ArgError("label_datatype must be 2 (UINT8) or 7 (FLOAT32)");
+        Pose p;
+        double ti = 0, ta = 0;
+        h->impl->register_frame_pointcloud2(data, n_points, point_step, x_offset, y_offset, z_offset, label_offset, label_datatype == 7,
+                                            timestamps, p, ti, ta);
+        pose_to_wire(p, pose_out);
+        if (t_icp) *t_icp = ti;
+        if (t_all) *t_all = ta;
+        return 0;
+    });
+}
 int64_t sage_last_source(sage_pipeline *h, double *out, size_t cap) {
     return guarded([&] {
         if (!out) return (long long)h->impl->n_source();

@@ -216,6 +216,22 @@ __global__ void scan_add_kernel(uint32_t *pos, const uint32_t *block_sums, uint3
     if (i < n) pos[i] += block_sums[i / 1024u];
 }
 
+// one thread per point; fields may sit at any byte offset (the reference's message is a packed 17-byte record:
+// f32 x, y, z @0/4/8, u8 label @12, u32 rgb @13 — eval/kitti_pub.py:184-207), so they are assembled from bytes
+__device__ __forceinline__ float load_f32_unaligned(const uint8_t *p) {
+    const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    return __uint_as_float(v);
+}
+__global__ void unpack_pointcloud2_kernel(const uint8_t *data, uint32_t n, uint32_t step, uint32_t xo, uint32_t yo, uint32_t zo, uint32_t lo,
+                                          int label_is_f32, double4 *out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *r = data + (size_t)i * step;
+    // points.emplace_back(*msg_x, *msg_y, *msg_z, *msg_l): f32 / u8 widened to f64 (ros/ros2/Utils.hpp:170,176)
+    const double l = label_is_f32 ? (double)load_f32_unaligned(r + lo) : (double)r[lo];
+    out[i] = make_double4((double)load_f32_unaligned(r + xo), (double)load_f32_unaligned(r + yo), (double)load_f32_unaligned(r + zo), l);
+}
+
 __global__ void deskew_kernel(const double4 *in, const double *ts, uint32_t n, double d0, double d1, double d2, double d3, double d4,
                               double d5, double4 *out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -312,6 +328,14 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
     SAGE_LAUNCH(ds_gather_kernel, fe_blocks(m), kFeThreads, 0, stream_, in, widx_.p, perm_.p, crop, out, (uint32_t)m);
     SAGE_CUDA(cudaStreamSynchronize(stream_));  // perm_pin_ is reused by the next call
     return m;
+}
+
+void FrontEnd::unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,
+                                  uint32_t label_off, int label_is_f32, double4 *out) {
+    SAGE_CUDA(cudaSetDevice(device_));
+    if (n == 0) return;
+    SAGE_LAUNCH(unpack_pointcloud2_kernel, fe_blocks(n), kFeThreads, 0, stream_, data_dev, (uint32_t)n, point_step, x_off, y_off, z_off, label_off,
+                label_is_f32, out);
 }
 
 void FrontEnd::deskew(const double4 *in, const double *ts, size_t n, const Pose &start, const Pose &finish, double4 *out) {

@@ -37,6 +37,9 @@ public:
     size_t downsample(const double4 *in, size_t n, double vox_scale, const CropParams &crop, double4 *out);
     // Preprocess only (order-preserving compaction).  Returns kept count.  Synchronises.
     size_t preprocess(const double4 *in, size_t n, const CropParams &crop, double4 *out);
+    // utils::PointCloud2ToEigen (ros/ros2/Utils.hpp:161-180) on the device: packed records -> x, y, z, label as f64
+    void unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,
+                            uint32_t label_off, int label_is_f32, double4 *out);
     // DeSkewScan on the device (in place allowed).
     void deskew(const double4 *in, const double *timestamps_dev, size_t n, const Pose &start, const Pose &finish, double4 *out);
 

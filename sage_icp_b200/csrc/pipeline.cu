@@ -115,8 +115,25 @@ void Pipeline::fetch(const double4 *dev, size_t n, std::vector<double> &out) {
 
 // RegisterFrame — pipeline/sageICP.cpp:36-52 (deskew wrapper) and :54-95
 void Pipeline::register_frame(const double *xyzl, size_t n, const double *timestamps, Pose &pose_out, double &t_icp, double &t_all) {
+    register_frame_dev(map_.stage_points(xyzl, n), n, timestamps, pose_out, t_icp, t_all);
+}
+
+void Pipeline::register_frame_pointcloud2(const uint8_t *data, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,
+                                          uint32_t label_off, int label_is_f32, const double *timestamps, Pose &pose_out, double &t_icp,
+                                          double &t_all) {
+    const uint32_t need = (label_is_f32 ? 4u : 1u);
+    if (point_step == 0 || x_off + 4 > point_step || y_off + 4 > point_step || z_off + 4 > point_step || label_off + need > point_step)
+        throw ArgError("PointCloud2 field offsets do not fit point_step");
+    SAGE_CUDA(cudaSetDevice(map_.device()));
+    packed_.ensure(n * (size_t)point_step + 1);
+    unpacked_.ensure(n ? n : 1);
+    if (n) SAGE_CUDA(cudaMemcpyAsync(packed_.p, data, n * (size_t)point_step, cudaMemcpyHostToDevice, map_.stream()));
+    fe_.unpack_pointcloud2(packed_.p, n, point_step, x_off, y_off, z_off, label_off, label_is_f32, unpacked_.p);
+    register_frame_dev(unpacked_.p, n, timestamps, pose_out, t_icp, t_all);
+}
+
+void Pipeline::register_frame_dev(const double4 *raw, size_t n, const double *timestamps, Pose &pose_out, double &t_icp, double &t_all) {
     using clock = std::chrono::high_resolution_clock;
-    const double4 *raw = map_.stage_points(xyzl, n);
     if (cfg_.deskew && timestamps && poses_.size() > 2) {  // pipeline/sageICP.cpp:39-49
         ts_.ensure(n ? n : 1);
         deskewed_.ensure(n ? n : 1);

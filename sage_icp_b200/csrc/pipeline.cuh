@@ -13,6 +13,10 @@ public:
     Pipeline(const sage_config_pod &config, int device);
 
     void register_frame(const double *xyzl, size_t n, const double *timestamps, Pose &pose_out, double &t_icp, double &t_all);
+    // RegisterFrame fed with the raw sensor_msgs/PointCloud2 data buffer (host): unpacked on the device
+    void register_frame_pointcloud2(const uint8_t *data, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,
+                                    uint32_t label_off, int label_is_f32, const double *timestamps, Pose &pose_out, double &t_icp,
+                                    double &t_all);
     void voxelize_host(const double *xyzl, size_t n, std::vector<double> &source, std::vector<double> &downsample);
     double get_adaptive_threshold();
     bool has_moved();
@@ -32,6 +36,7 @@ public:
 
 private:
     void voxelize_dev(const double4 *frame, size_t n, const CropParams &cp);
+    void register_frame_dev(const double4 *raw, size_t n, const double *timestamps, Pose &pose_out, double &t_icp, double &t_all);
     void fetch(const double4 *dev, size_t n, std::vector<double> &out);
     double compute_threshold();
     void reset_threshold();
@@ -48,6 +53,8 @@ private:
 
     DevBuf<double4> ds_, src_, tmp_, deskewed_;
     DevBuf<double> ts_;
+    DevBuf<uint8_t> packed_;
+    DevBuf<double4> unpacked_;
     size_t n_ds_ = 0, n_src_ = 0;
     int last_iters_ = 0;
     double last_sigma_ = 0;

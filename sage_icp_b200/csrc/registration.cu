@@ -27,7 +27,11 @@
 
 namespace sage {
 
-constexpr int kNnThreads = 256;
+#ifndef SAGE_NN_THREADS
+#define SAGE_NN_THREADS 256
+#endif
+constexpr int kNnThreads = SAGE_NN_THREADS;
+static_assert(kNnThreads % 32 == 0 && (kNnThreads / 32) * 3 >= 17, "the last-block reduction gives each warp up to three of the 17 sums");
 constexpr int kSums = 17;
 constexpr int kDbg = 12;  // debug timeline stamps per block
 
@@ -242,11 +246,11 @@ __device__ __forceinline__ void rank_record(const float4 h, uint32_t idx, float 
 #ifndef SAGE_LIGHT_MINB
 #define SAGE_LIGHT_MINB 4
 #endif
-__device__ __forceinline__ void scan_voxel_thread(const float4 *__restrict__ hot, uint32_t base_idx, uint32_t cnt, float rx, float ry, float rz,
-                                                  float qlf, float th32, float &min1, float &min2, uint32_t &idx1, bool &odd) {
+// one thread scans one voxel, SAGE_SCAN_UNROLL independent 16-byte loads in flight.  (Measured on B200: deeper unrolling
+// or a software pipeline across batches costs more in spills than it hides — profiles/r01b_search_kernel_timeline.md.)
+__device__ __forceinline__ void scan_voxel_thread(const float4 *__restrict__ hot, uint32_t base_idx, uint32_t cnt, float rx, float ry,
+                                                  float rz, float qlf, float th32, float &min1, float &min2, uint32_t &idx1, bool &odd) {
     constexpr int U = SAGE_SCAN_UNROLL;
-    // a voxel's records span up to 5 128-byte lines: start them all now so that the loop below misses L1 only once
-    for (uint32_t l = 8; l < cnt; l += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(hot + base_idx + l));
     uint32_t j = 0;
     for (; j + U <= cnt; j += U) {
         float4 h[U];

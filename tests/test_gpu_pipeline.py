@@ -105,3 +105,36 @@ def test_bad_config_fails_loudly(cfg):
         sg.SagePipeline(SageConfig())  # empty voxel_labels: UB in the reference, error here
     with pytest.raises(sg.SageError):
         sg.SagePipeline(launch_config(dynamic_vehicle_filter=True))
+
+
+def _pointcloud2_buffer(scan, label_f32=False):
+    """The reference publishers' wire format (eval/kitti_pub.py:184-207): packed structured records."""
+    fields = [("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("label", "<f4" if label_f32 else "u1"), ("rgb", "<u4")]
+    rec = np.zeros(len(scan), dtype=np.dtype(fields))  # packed: itemsize 17 (u8 label) / 20 (f32 label)
+    rec["x"], rec["y"], rec["z"] = scan[:, 0], scan[:, 1], scan[:, 2]
+    rec["label"] = scan[:, 3]
+    rec["rgb"] = 0x00ff00
+    return rec.view(np.uint8).reshape(-1), rec.dtype.itemsize
+
+
+@pytest.mark.parametrize("label_f32", [False, True])
+def test_register_frame_from_pointcloud2_buffer(orc, cfg, label_f32):
+    """utils::PointCloud2ToEigen (ros/ros2/Utils.hpp:161-180) done on the device: feeding the raw message buffer gives the same
+    poses, bit for bit, as widening on the host and calling RegisterFrame(points); and both match the oracle."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    a, b, o = sg.SagePipeline(cfg), sg.SagePipeline(cfg), orc.OraclePipeline(cfg, evict_faithful=False)
+    traj = syn.trajectory(6)
+    for i in range(6):
+        scan = syn.make_scan(500 + i, tuple(traj[i]), n_beams=32, n_az=700)
+        buf, step = _pointcloud2_buffer(scan, label_f32)
+        assert step == (20 if label_f32 else 17)
+        pa, _, _ = a.register_frame_pointcloud2(buf, len(scan), step, (0, 4, 8, 12), 7 if label_f32 else 2)
+        pb, _, _ = b.register_frame(scan)
+        po, _, _ = o.register_frame(scan)
+        assert np.array_equal(pa, pb), i
+        assert np.array_equal(a.last_source(), b.last_source())
+        dt, da = pose_delta(pa, po)
+        assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD
+    with pytest.raises(sg.SageError):
+        a.register_frame_pointcloud2(buf, len(scan), 10, (0, 4, 8, 12), 2)  # offsets do not fit point_step

@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout=400 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -8 gpurun_out/pytest_gpu.log
-timeout 200 python tools/perf_probe.py 2>&1 | tee gpurun_out/perf_probe.log | grep -E "rep 2|timeline"
-timeout 600 python tools/stream_bench.py --frames 300 --cpu-frames 30 > gpurun_out/stream.json 2> gpurun_out/stream.err; echo rc=$?; cat gpurun_out/stream.json; tail -3 gpurun_out/stream.err
+timeout 300 python -m pytest tests/test_gpu_core.py tests/test_gpu_search_exactness.py -m gpu -x -q --timeout=60 --timeout-method=thread 2>&1 | tail -2
+echo "== default"; timeout 200 python tools/perf_probe.py 2>&1 | grep -E "rep 2|timeline|phase"
+for v in t256_u2 t256_u6; do echo "== variant $v"; SAGE_ICP_LIB=$PWD/sage_icp_b200/lib/variant_$v.so timeout 200 python tools/perf_probe.py 2>&1 | grep -E "rep 2|timeline|home scanned|neighbours"; done

@@ -123,6 +123,15 @@ class ClockSampler:
         return out
 
 
+_OUT = None
+
+
+def emit(text: str):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -153,7 +162,7 @@ def run_reference(args):
     ms = 1e3 * float(np.mean(times))
     v = 1e3 / ms
     sample = f"{args.steps} scans, every {max(1, int(round(1 / frac)))}-th query of each 120k-pt scan x {ITERS} GN iters, time scaled to the full scan"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "RegisterFrame scans/sec (120 k-pt labeled scan)", "value": v, "unit": "scans/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -164,7 +173,9 @@ def run_reference(args):
 
 
 def workload_config(args, map_points, map_voxels):
-    return {"workload": "BASELINE configs[1]: 120k-pt labelled scan as direct queries vs pre-built voxel map, 10 GN iterations "
+    rays = args.beams * args.az
+    which = "configs[1]: 120k-pt" if rays == 120000 else f"configs[3]-style: {rays // 1000}k-pt dense"
+    return {"workload": f"BASELINE {which} labelled scan as direct queries vs pre-built voxel map, 10 GN iterations "
                         "(kernel-level sage_icp::RegisterFrame)",
             "scan_rays": args.beams * args.az, "map_points": int(map_points), "map_voxels": int(map_voxels), "gn_iterations": ITERS,
             "max_correspondence_distance": MAX_DIST, "kernel": KERNEL, "sem_th": SEM_TH,
@@ -173,6 +184,13 @@ def workload_config(args, map_points, map_voxels):
 
 
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under torchrun) is sent to
+    # stderr instead, and the line itself goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -349,7 +367,7 @@ def main():
                                                "requested_bytes": 16 * (work[0] + work[1]) / n_work + 32 + 32 + 32}},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -202,7 +202,8 @@ __global__ void scan_block_kernel(const uint32_t *flags, uint32_t *pos, uint32_t
         if (base + k < n) pos[base + k] = excl + e[k];
     if (threadIdx.x == kFeThreads - 1) block_sums[blockIdx.x] = s[threadIdx.x];
 }
-__global__ void scan_sums_kernel(uint32_t *block_sums, uint32_t nb, uint32_t *total) {
+__global__ void scan_sums_kernel(uint32_t *block_sums, uint32_t nb, uint32_t *total, const uint32_t *err) {
+    if (err) total[1] = *err;
     uint32_t run = 0;
     for (uint32_t b = 0; b < nb; ++b) {
         const uint32_t v = block_sums[b];
@@ -253,12 +254,12 @@ FrontEnd::FrontEnd(const GroupTable &groups, int device, cudaStream_t stream) : 
     total_pin_.ensure(2);
 }
 
-void FrontEnd::scan_flags(size_t n) {
+void FrontEnd::scan_flags(size_t n, uint32_t *total_out, const uint32_t *err) {
     const unsigned nb = fe_blocks(n, 1024);
     block_sums_.ensure(nb);
     pos_.ensure(n);
     SAGE_LAUNCH(scan_block_kernel, nb, kFeThreads, 0, stream_, flags_.p, pos_.p, block_sums_.p, (uint32_t)n);
-    SAGE_LAUNCH(scan_sums_kernel, 1, 1, 0, stream_, block_sums_.p, nb, total_.p);
+    SAGE_LAUNCH(scan_sums_kernel, 1, 1, 0, stream_, block_sums_.p, nb, total_out, err);
     SAGE_LAUNCH(scan_add_kernel, fe_blocks(n), kFeThreads, 0, stream_, pos_.p, block_sums_.p, (uint32_t)n);
 }
 
@@ -267,7 +268,7 @@ size_t FrontEnd::preprocess(const double4 *in, size_t n, const CropParams &crop,
     if (n == 0) return 0;
     flags_.ensure(n);
     SAGE_LAUNCH(crop_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, (uint32_t)n, crop, flags_.p);
-    scan_flags(n);
+    scan_flags(n, total_.p, nullptr);
     SAGE_LAUNCH(crop_scatter_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, (uint32_t)n, crop, flags_.p, pos_.p, out);
     SAGE_CUDA(cudaMemcpyAsync(total_pin_.p, total_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
     SAGE_CUDA(cudaStreamSynchronize(stream_));
@@ -287,25 +288,25 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
     slot_.ensure(n);
     flags_.ensure(n);
     widx_.ensure(n);
-    whash_.ensure(n);
-    perm_.ensure(n);
+    // Host-visible results live in pinned memory that the kernels write / read directly (zero copy), so one stream
+    // synchronisation per call is enough: [count, range errors] + the survivors' hashes out, the permutation back in.
+    // Two permutation buffers alternate between calls: the gather of call k may still be running when call k+1 fills its own.
     whash_pin_.ensure(n);
-    perm_pin_.ensure(n);
+    perm_pin_[parity_].ensure(n);  // this buffer's last reader (two calls ago) finished before the previous call's synchronisation
+    uint32_t *perm_host = perm_pin_[parity_].p;
+    parity_ ^= 1;
+    SAGE_CUDA(cudaMemsetAsync(total_.p, 0, 2 * sizeof(uint32_t), stream_));
     SAGE_CUDA(cudaMemsetAsync(tkey_.p, 0xff, (size_t)cap * sizeof(unsigned long long), stream_));
     SAGE_CUDA(cudaMemsetAsync(tfirst_.p, 0xff, (size_t)cap * sizeof(uint32_t), stream_));
-    SAGE_CUDA(cudaMemsetAsync(total_.p, 0, 2 * sizeof(uint32_t), stream_));
     SAGE_LAUNCH(ds_insert_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, (uint32_t)n, groups_, crop, vox_scale, tkey_.p, tfirst_.p,
                 cap - 1, slot_.p, total_.p + 1);
     SAGE_LAUNCH(ds_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, slot_.p, tfirst_.p, flags_.p, (uint32_t)n);
-    scan_flags(n);
-    SAGE_LAUNCH(ds_collect_kernel, fe_blocks(n), kFeThreads, 0, stream_, slot_.p, flags_.p, pos_.p, tkey_.p, widx_.p, whash_.p, (uint32_t)n);
-    SAGE_CUDA(cudaMemcpyAsync(total_pin_.p, total_.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    scan_flags(n, total_pin_.p, total_.p + 1);  // count and range-error flag land in pinned memory
+    SAGE_LAUNCH(ds_collect_kernel, fe_blocks(n), kFeThreads, 0, stream_, slot_.p, flags_.p, pos_.p, tkey_.p, widx_.p, whash_pin_.p, (uint32_t)n);
     SAGE_CUDA(cudaStreamSynchronize(stream_));
     if (total_pin_.p[1]) throw ArgError("VoxelDownsample: point/voxel_size outside the +-2^19 voxel range");
     const size_t m = total_pin_.p[0];
     if (m == 0) return 0;
-    SAGE_CUDA(cudaMemcpyAsync(whash_pin_.p, whash_.p, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-    SAGE_CUDA(cudaStreamSynchronize(stream_));
 
     // per group: replay the robin_map on the distinct keys (first-index order) and emit groups in index order
     // (core/Preprocessing.cpp:76-82)
@@ -320,14 +321,12 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
                 seq_scratch_.push_back(whash_pin_.p[j] & 0xfffffu);
             }
         if (members.empty()) continue;
-        std::vector<uint32_t> ord(members.size());
-        robin_iteration_order(seq_scratch_.data(), seq_scratch_.size(), ord.data());
-        for (size_t k = 0; k < ord.size(); ++k) perm_pin_.p[o++] = members[ord[k]];
+        ord_scratch_.resize(members.size());
+        robin_iteration_order(seq_scratch_.data(), seq_scratch_.size(), ord_scratch_.data());
+        for (size_t k = 0; k < ord_scratch_.size(); ++k) perm_host[o++] = members[ord_scratch_[k]];
     }
-    SAGE_CUDA(cudaMemcpyAsync(perm_.p, perm_pin_.p, m * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
-    SAGE_LAUNCH(ds_gather_kernel, fe_blocks(m), kFeThreads, 0, stream_, in, widx_.p, perm_.p, crop, out, (uint32_t)m);
-    SAGE_CUDA(cudaStreamSynchronize(stream_));  // perm_pin_ is reused by the next call
-    return m;
+    SAGE_LAUNCH(ds_gather_kernel, fe_blocks(m), kFeThreads, 0, stream_, in, widx_.p, perm_host, crop, out, (uint32_t)m);
+    return m;  // `out` is valid in stream order; callers that read it on the host synchronise themselves
 }
 
 void FrontEnd::unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,

@@ -44,7 +44,7 @@ public:
     void deskew(const double4 *in, const double *timestamps_dev, size_t n, const Pose &start, const Pose &finish, double4 *out);
 
 private:
-    void scan_flags(size_t n);  // exclusive scan of flags_ -> pos_, total -> total_ (device)
+    void scan_flags(size_t n, uint32_t *total_out, const uint32_t *err);  // exclusive scan of flags_ -> pos_, total -> *total_out (device or mapped pinned)
 
     GroupTable groups_;
     int device_;
@@ -54,8 +54,9 @@ private:
     uint32_t tcap_ = 0;
     DevBuf<uint32_t> slot_, flags_, pos_, block_sums_, widx_, whash_, perm_;
     DevBuf<uint32_t> total_;
-    PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_;
-    std::vector<uint32_t> order_scratch_, seq_scratch_;
+    PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_[2];
+    int parity_ = 0;
+    std::vector<uint32_t> order_scratch_, seq_scratch_, ord_scratch_;
 };
 
 }  // namespace sage

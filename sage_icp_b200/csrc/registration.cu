@@ -794,9 +794,13 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     src_.ensure(n ? n : 1);
     if (n) SAGE_CUDA(cudaMemcpyAsync(src_.p, frame, n * sizeof(double4), cudaMemcpyDeviceToDevice, stream_));
     SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, guess, max_iters, est_th);
+    // iterations are launched in batches (kernels of a finished registration return at once) and `done` is polled between
+    // batches; the first batch is sized from the previous registration so that the common case needs one round trip
     int launched = 0;
     while (launched < max_iters) {
-        const int batch = (max_iters - launched) < 8 ? (max_iters - launched) : 8;
+        int batch = launched == 0 ? (last_iters_ + 2 > 8 ? last_iters_ + 2 : 8) : 8;
+        if (batch > 48) batch = 48;
+        if (batch > max_iters - launched) batch = max_iters - launched;
         for (int b = 0; b < batch; ++b) launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr);
         launched += batch;
         SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
@@ -804,6 +808,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
         if (icp_pin_.p->done) break;
     }
     pose_out = icp_pin_.p->result;
+    last_iters_ = icp_pin_.p->iter;
     return icp_pin_.p->iter;
 }
 

@@ -20,63 +20,72 @@ static inline unsigned fe_blocks(size_t n, int per_block = kFeThreads) { return 
 // host: tsl::robin_map v1.0.1 iteration-order replay for distinct keys
 
 void robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out) {
-    // bucket arrays: dist (-1 = empty) and payload (input position)
-    std::vector<int16_t> dist, ndist;
-    std::vector<uint32_t> val, nval;
+    // One 64-bit word per bucket: [63:48] distance from the ideal bucket (0xffff = empty), [47:28] the key's 20-bit hash,
+    // [27:0] payload (input position).  Two preallocated arrays alternate across growth generations.
+    if (n >= (1u << 28)) throw ArgError("robin_iteration_order: too many keys");
+    constexpr uint64_t kEmpty = ~0ull;
+    constexpr int kDistLimit = 8192;
+    static thread_local std::vector<uint64_t> buf[2];
+    size_t final_cap = 2;
+    while (final_cap < 2 * n) final_cap *= 2;
+    final_cap *= 2;  // a probe-length-forced growth (hash saturation) may add one generation
+    for (auto &b : buf)
+        if (b.size() < final_cap) b.resize(final_cap);
+    uint64_t *cur = buf[0].data(), *nxt = buf[1].data();
     size_t B = 0, mask = 0, size = 0, load_threshold = 0;
     bool grow_next = false;
-    constexpr int kDistLimit = 8192;
+    auto dist_of = [](uint64_t e) { return e == kEmpty ? -1 : (int)(e >> 48); };
+    auto make = [](int d, uint64_t rest) { return ((uint64_t)d << 48) | rest; };  // rest = hash << 28 | val
 
-    auto place = [&](std::vector<int16_t> &D, std::vector<uint32_t> &V, size_t msk, size_t ib, int d, uint32_t v, bool track) {
-        // robin-hood swap-and-carry from bucket ib with distance d
+    // robin-hood swap-and-carry of `rest` from bucket ib with distance d
+    auto place = [&](uint64_t *T, size_t msk, size_t ib, int d, uint64_t rest, bool track) {
         while (true) {
-            if (d > D[ib]) {
-                if (D[ib] < 0) {
-                    D[ib] = (int16_t)d, V[ib] = v;
-                    return;
-                }
+            const uint64_t e = T[ib];
+            const int ed = dist_of(e);
+            if (d > ed) {
+                T[ib] = make(d, rest);
+                if (ed < 0) return;
                 if (track && d >= kDistLimit) grow_next = true;
-                const int od = D[ib];
-                const uint32_t ov = V[ib];
-                D[ib] = (int16_t)d, V[ib] = v;
-                d = od, v = ov;
+                d = ed, rest = e & 0xffffffffffffull;
             }
             ++d;
             ib = (ib + 1) & msk;
         }
     };
     auto rehash = [&](size_t count) {
-        ndist.assign(count, (int16_t)-1);
-        nval.assign(count, 0u);
+        if (count > final_cap) throw ArgError("robin_iteration_order: table growth beyond the preallocated generations");
+        std::fill(nxt, nxt + count, kEmpty);
         const size_t nmask = count - 1;
         for (size_t b = 0; b < B; ++b)
-            if (dist[b] >= 0) place(ndist, nval, nmask, hash20[val[b]] & nmask, 0, val[b], false);
-        dist.swap(ndist);
-        val.swap(nval);
+            if (cur[b] != kEmpty) {
+                const uint64_t rest = cur[b] & 0xffffffffffffull;
+                place(nxt, nmask, (size_t)(rest >> 28) & nmask, 0, rest, false);
+            }
+        std::swap(cur, nxt);
         B = count, mask = nmask;
         load_threshold = (size_t)((float)count * 0.5f);
     };
 
     for (size_t i = 0; i < n; ++i) {
-        const uint32_t h = hash20[i];
+        const uint32_t h = hash20[i] & 0xfffffu;
         size_t ib = 0;
         int d = 0;
         if (B) {
             ib = h & mask;
-            while (d <= dist[ib]) ib = (ib + 1) & mask, ++d;
+            while (d <= dist_of(cur[ib])) ib = (ib + 1) & mask, ++d;
         }
         while (grow_next || d > kDistLimit || size >= load_threshold) {
             rehash(B ? B * 2 : 2);
             grow_next = false;
             ib = h & mask, d = 0;
-            while (d <= dist[ib]) ib = (ib + 1) & mask, ++d;
+            while (d <= dist_of(cur[ib])) ib = (ib + 1) & mask, ++d;
         }
-        place(dist, val, mask, ib, d, (uint32_t)i, true);
+        place(cur, mask, ib, d, ((uint64_t)h << 28) | (uint64_t)i, true);
         ++size;
     }
     size_t k = 0;
     for (size_t b = 0; b < B; ++b)
-        if (dist[b] >= 0) order_out[k++] = val[b];
+        if (cur[b] != kEmpty) order_out[k++] = (uint32_t)(cur[b] & 0xfffffffu);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -309,22 +318,26 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
     if (m == 0) return 0;
 
     // per group: replay the robin_map on the distinct keys (first-index order) and emit groups in index order
-    // (core/Preprocessing.cpp:76-82)
-    size_t o = 0;
-    for (int g = 0; g < groups_.n_groups; ++g) {
-        seq_scratch_.clear();
-        order_scratch_.clear();
-        std::vector<uint32_t> &members = order_scratch_;
-        for (size_t j = 0; j < m; ++j)
-            if ((whash_pin_.p[j] >> 20) == (uint32_t)g) {
-                members.push_back((uint32_t)j);
-                seq_scratch_.push_back(whash_pin_.p[j] & 0xfffffu);
-            }
-        if (members.empty()) continue;
-        ord_scratch_.resize(members.size());
-        robin_iteration_order(seq_scratch_.data(), seq_scratch_.size(), ord_scratch_.data());
-        for (size_t k = 0; k < ord_scratch_.size(); ++k) perm_host[o++] = members[ord_scratch_[k]];
+    // (core/Preprocessing.cpp:76-82).  Groups are independent tables: they are replayed side by side on host threads.
+    const int G = groups_.n_groups;
+    group_members_.resize(G);
+    group_hashes_.resize(G);
+    group_order_.resize(G);
+    for (int g = 0; g < G; ++g) group_members_[g].clear(), group_hashes_[g].clear();
+    for (size_t j = 0; j < m; ++j) {
+        const uint32_t w = whash_pin_.p[j], g = w >> 20;
+        group_members_[g].push_back((uint32_t)j);
+        group_hashes_[g].push_back(w & 0xfffffu);
     }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(G < 6 ? G : 6) if (m > 1500)
+    for (int g = 0; g < G; ++g) {
+        group_order_[g].resize(group_members_[g].size());
+        if (!group_members_[g].empty())
+            robin_iteration_order(group_hashes_[g].data(), group_hashes_[g].size(), group_order_[g].data());
+    }
+    size_t o = 0;
+    for (int g = 0; g < G; ++g)
+        for (size_t k = 0; k < group_order_[g].size(); ++k) perm_host[o++] = group_members_[g][group_order_[g][k]];
     SAGE_LAUNCH(ds_gather_kernel, fe_blocks(m), kFeThreads, 0, stream_, in, widx_.p, perm_host, crop, out, (uint32_t)m);
     return m;  // `out` is valid in stream order; callers that read it on the host synchronise themselves
 }

@@ -56,7 +56,7 @@ private:
     DevBuf<uint32_t> total_;
     PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_[2];
     int parity_ = 0;
-    std::vector<uint32_t> order_scratch_, seq_scratch_, ord_scratch_;
+    std::vector<std::vector<uint32_t>> group_members_, group_hashes_, group_order_;
 };
 
 }  // namespace sage

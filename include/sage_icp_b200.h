@@ -169,7 +169,8 @@ int sage_core_normal_equations(sage_map *m, const double *frame_xyzl, size_t n, 
                                double kernel, double sem_th, double JTJ_out[36], double JTr_out[6],
                                int64_t *n_pairs_out);
 
-/* sage_icp::Preprocess, range branch — core/Preprocessing.cpp:173-187.  Returns the kept count. */
+/* sage_icp::Preprocess — core/Preprocessing.cpp:86-189: the range branch (:173-187), or the dynamic-vehicle branch (:95-172)
+ * when the pipeline's config has dynamic_vehicle_filter set.  Returns the kept count. */
 int64_t sage_preprocess(sage_pipeline *h, const double *xyzl, size_t n, double *out, size_t cap_points);
 /* sage_icp::VoxelDownsample — core/Preprocessing.cpp:44-84 (reference output order). */
 int64_t sage_voxel_downsample(sage_pipeline *h, const double *xyzl, size_t n, double vox_scale, double *out,

@@ -117,6 +117,12 @@ size_t orc_preprocess(const double *xyzl, size_t n, double max_range, double min
                       double *out, size_t cap) {
     return from_cloud(Preprocess(to_cloud(xyzl, n), max_range, min_range, label_max_range), out, cap);
 }
+size_t orc_preprocess_dynamic(const orc_config_pod *cfg, const double *xyzl, size_t n, double *out, size_t cap) {
+    const Config c = to_config(cfg);
+    return from_cloud(PreprocessDynamic(to_cloud(xyzl, n), c.max_range, c.min_range, c.label_max_range, c.dynamic_vehicle_filter_th,
+                                        c.voxel_labels[(size_t)c.dynamic_vehicle_voxid], c.dynamic_remove_lankmark),
+                      out, cap);
+}
 size_t orc_voxel_downsample(const orc_config_pod *cfg, const double *xyzl, size_t n, double vox_scale, double *out, size_t cap) {
     const Config c = to_config(cfg);
     return from_cloud(VoxelDownsample(to_cloud(xyzl, n), c.voxel_labels, c.voxel_size, vox_scale), out, cap);

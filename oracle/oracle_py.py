@@ -38,7 +38,7 @@ def lib() -> C.CDLL:
         L.orc_create.restype = C.c_void_p
         L.orc_map_create.restype = C.c_void_p
         L.orc_pipeline_map.restype = C.c_void_p
-        for f in ("orc_preprocess", "orc_voxel_downsample", "orc_map_num_voxels", "orc_map_bucket_count", "orc_map_num_points",
+        for f in ("orc_preprocess", "orc_preprocess_dynamic", "orc_voxel_downsample", "orc_map_num_voxels", "orc_map_bucket_count", "orc_map_num_points",
                   "orc_map_pointcloud", "orc_map_dump", "orc_map_get_correspondences", "orc_last_source",
                   "orc_last_frame_downsample", "orc_num_poses", "orc_local_map", "orc_robin_order", "orc_voxelize", "orc_deskew"):
             getattr(L, f).restype = C.c_size_t
@@ -109,6 +109,13 @@ def preprocess(pts, max_range, min_range, label_max_range) -> np.ndarray:
     pts = _c64(pts); out = np.empty_like(pts)
     n = lib().orc_preprocess(_d(pts), C.c_size_t(len(pts)), C.c_double(max_range), C.c_double(min_range),
                              C.c_double(label_max_range), _d(out), C.c_size_t(len(pts)))
+    return out[:n].copy()
+
+
+def preprocess_dynamic(cfg, pts) -> np.ndarray:
+    """Preprocess with the dynamic-vehicle filter on (core/Preprocessing.cpp:95-172)."""
+    pod = cfg.to_pod(); pts = _c64(pts); out = np.empty_like(pts)
+    n = lib().orc_preprocess_dynamic(C.byref(pod), _d(pts), C.c_size_t(len(pts)), _d(out), C.c_size_t(len(pts)))
     return out[:n].copy()
 
 

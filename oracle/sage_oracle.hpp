@@ -75,6 +75,70 @@ inline Cloud Preprocess(const Cloud &frame, double max_range, double min_range, 
     return inliers;
 }
 
+// Preprocess, dynamic-vehicle branch — core/Preprocessing.cpp:95-172.  The reference leans on PCL (absent here):
+// EuclideanClusterExtraction (tolerance 0.5 m, min 5 points) over the vehicle-labelled points and a FLANN radius search
+// (0.5 m) for landmark-labelled points around every cluster point, all on float32 coordinates.  Restated from PCL's
+// published behaviour: a cluster is a connected component of the graph "squared f32 distance < 0.5^2" (FLANN's radius
+// result set keeps dist < radius); a cluster is kept (static vehicle) iff the landmark hits summed over its points exceed
+// int(dy_th * size) — the reference's early `break` only short-circuits that monotone count.
+// PARITY UNPINNED, and one documented difference: the kept clusters' points are appended in INPUT order, whereas PCL emits
+// clusters by descending size (std::sort, ties unspecified) and points in breadth-first order of its kd-tree queries.  The
+// retained point SET is the reference's; the order of the appended vehicle points is this restatement's.
+inline Cloud PreprocessDynamic(const Cloud &frame, double max_range, double min_range, double label_max_range, double dy_th,
+                               const std::vector<int> &dynamic_labels, const std::vector<int> &lankmark) {
+    struct P {
+        float x, y, z;
+        uint32_t label;
+    };
+    Cloud inliers, vehicle_inliers;
+    std::vector<P> all, veh;
+    for (const auto &point : frame) {
+        Point4 point_new = point;
+        const double nrm = norm(xyz(point));
+        if (nrm < max_range && nrm > min_range) {
+            if (nrm > label_max_range) point_new.l = 0.0;
+            const P t{(float)point.x, (float)point.y, (float)point.z, (uint32_t)point_new.l};
+            all.push_back(t);
+            if (std::find(dynamic_labels.begin(), dynamic_labels.end(), (int)t.label) != dynamic_labels.end()) {
+                veh.push_back(t);
+                vehicle_inliers.push_back(point_new);
+            } else {
+                inliers.push_back(point_new);
+            }
+        }
+    }
+    auto near = [](const P &a, const P &b) {
+        const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+        return (dx * dx + dy * dy) + dz * dz < 0.25f;
+    };
+    // connected components (brute force; the oracle favours obviousness over speed)
+    const size_t nv = veh.size();
+    std::vector<int> comp(nv, -1);
+    std::vector<std::vector<size_t>> clusters;
+    for (size_t s0 = 0; s0 < nv; ++s0) {
+        if (comp[s0] >= 0) continue;
+        std::vector<size_t> members{s0};
+        comp[s0] = (int)clusters.size();
+        for (size_t h = 0; h < members.size(); ++h)
+            for (size_t j = 0; j < nv; ++j)
+                if (comp[j] < 0 && near(veh[members[h]], veh[j])) comp[j] = (int)clusters.size(), members.push_back(j);
+        clusters.push_back(std::move(members));
+    }
+    std::vector<char> keep(nv, 0);
+    for (const auto &members : clusters) {
+        if (members.size() < 5) continue;  // setMinClusterSize(5)
+        long long count = 0;
+        for (size_t i : members)
+            for (const auto &q : all)
+                if (std::find(lankmark.begin(), lankmark.end(), (int)q.label) != lankmark.end() && near(veh[i], q)) ++count;
+        if (count > (long long)(int)(dy_th * (double)members.size()))
+            for (size_t i : members) keep[i] = 1;
+    }
+    for (size_t i = 0; i < nv; ++i)
+        if (keep[i]) inliers.push_back(vehicle_inliers[i]);
+    return inliers;
+}
+
 // VoxelDownsample — core/Preprocessing.cpp:44-84. The first `len` maps of grid_group are default-constructed
 // (bucket_count 0, unreserved, :50); the reserved copies appended at :52-56 are never used.
 inline Cloud VoxelDownsample(const Cloud &frame, const std::vector<std::vector<int>> &voxel_labels,
@@ -488,7 +552,11 @@ struct SageICP {
     // RegisterFrame(frame) — pipeline/sageICP.cpp:54-95; returns {source, t_icp, t_all}
     std::tuple<Cloud, double, double> RegisterFrame(const Cloud &frame) {
         auto t0 = std::chrono::high_resolution_clock::now();
-        const Cloud cropped = Preprocess(frame, config_.max_range, config_.min_range, config_.label_max_range);
+        const Cloud cropped = config_.dynamic_vehicle_filter
+                                  ? PreprocessDynamic(frame, config_.max_range, config_.min_range, config_.label_max_range,
+                                                      config_.dynamic_vehicle_filter_th, config_.voxel_labels[(size_t)config_.dynamic_vehicle_voxid],
+                                                      config_.dynamic_remove_lankmark)
+                                  : Preprocess(frame, config_.max_range, config_.min_range, config_.label_max_range);
         auto [source, frame_downsample] = Voxelize(cropped);
         const double sigma = GetAdaptiveThreshold();
         const SE3 prediction = GetPredictionModel();

@@ -226,6 +226,160 @@ __global__ void scan_add_kernel(uint32_t *pos, const uint32_t *block_sums, uint3
     if (i < n) pos[i] += block_sums[i / 1024u];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dynamic-vehicle filter (core/Preprocessing.cpp:95-172).  PCL's Euclidean cluster extraction is single linkage with
+// "squared float distance < tolerance^2", i.e. connected components; they are found with a 0.5 m cell grid and a lock-free
+// union-find whose roots are the smallest member index (so the result does not depend on scheduling).
+constexpr uint32_t kClsDrop = 0, kClsInlier = 1, kClsVehicle = 2, kClsLandmarkBit = 4;
+
+__device__ __forceinline__ bool dyn_near(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)) < 0.25f;  // 0.5 m, FLANN keeps dist < radius
+}
+__device__ __forceinline__ unsigned long long dyn_cell_key(int cx, int cy, int cz) {
+    return (unsigned long long)(uint32_t)(cx + kKeyBias) | ((unsigned long long)(uint32_t)(cy + kKeyBias) << kKeyBits) |
+           ((unsigned long long)(uint32_t)(cz + kKeyBias) << (2 * kKeyBits));
+}
+__device__ __forceinline__ int dyn_cell(float v) { return __float2int_rd(__fmul_rn(v, 2.0f)); }  // 0.5 m cells
+
+__device__ __forceinline__ uint32_t dyn_find_slot(const unsigned long long *keys, uint32_t mask, unsigned long long key) {
+    uint32_t sl = (uint32_t)mix64(key) & mask;
+    while (true) {
+        const unsigned long long cur = keys[sl];
+        if (cur == key) return sl;
+        if (cur == kEmptyKey) return kNil;
+        sl = (sl + 1) & mask;
+    }
+}
+
+// classify + put vehicle / landmark points on their cell's list
+__global__ void dyn_classify_kernel(const double4 *in, uint32_t n, CropParams crop, DynFilterParams dp, unsigned long long *keys, uint32_t mask,
+                                    uint32_t *head_v, uint32_t *head_l, uint32_t *next_v, uint32_t *next_l, uint32_t *parent, uint32_t *cls,
+                                    uint32_t *err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 p = in[i];
+    parent[i] = i;
+    if (!crop_point(crop, p)) {
+        cls[i] = kClsDrop;
+        return;
+    }
+    // point_temp.label = static_cast<uint32_t>(point_new[3]); membership tests on that integer (:108,:110,:155)
+    const int label = (int)(uint32_t)__double2uint_rz(p.w);
+    bool vehicle = false, landmark = false;
+    for (int k = 0; k < dp.n_dynamic; ++k) vehicle |= dp.dynamic_labels[k] == label;
+    for (int k = 0; k < dp.n_landmark; ++k) landmark |= dp.landmark_labels[k] == label;
+    cls[i] = (vehicle ? kClsVehicle : kClsInlier) | (landmark ? kClsLandmarkBit : 0u);
+    if (!vehicle && !landmark) return;
+    const float x = __double2float_rn(p.x), y = __double2float_rn(p.y), z = __double2float_rn(p.z);
+    const int cx = dyn_cell(x), cy = dyn_cell(y), cz = dyn_cell(z);
+    if (!key_in_range(cx, cy, cz)) {
+        atomicAdd(err, 1u);
+        return;
+    }
+    const unsigned long long key = dyn_cell_key(cx, cy, cz);
+    uint32_t sl = (uint32_t)mix64(key) & mask;
+    while (true) {
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(keys + sl);
+        if (cur == key) break;
+        if (cur == kEmptyKey) {
+            const unsigned long long old = atomicCAS(keys + sl, kEmptyKey, key);
+            if (old == kEmptyKey || old == key) break;
+        }
+        sl = (sl + 1) & mask;
+    }
+    if (vehicle) next_v[i] = atomicExch(head_v + sl, i);
+    if (landmark) next_l[i] = atomicExch(head_l + sl, i);
+}
+
+__device__ __forceinline__ uint32_t dyn_root(const uint32_t *parent, uint32_t a) {
+    while (true) {
+        const uint32_t pa = *reinterpret_cast<const volatile uint32_t *>(parent + a);
+        if (pa == a) return a;
+        a = pa;
+    }
+}
+
+// union every pair of vehicle points closer than 0.5 m; the smaller index becomes the root
+__global__ void dyn_union_kernel(const double4 *in, uint32_t n, const unsigned long long *keys, uint32_t mask, const uint32_t *head_v,
+                                 const uint32_t *next_v, uint32_t *parent, const uint32_t *cls) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (cls[i] & 3u) != kClsVehicle) return;
+    const double4 p = in[i];
+    const float x = __double2float_rn(p.x), y = __double2float_rn(p.y), z = __double2float_rn(p.z);
+    const int cx = dyn_cell(x), cy = dyn_cell(y), cz = dyn_cell(z);
+    for (int c = 0; c < 27; ++c) {
+        const int nx = cx + c / 9 - 1, ny = cy + (c / 3) % 3 - 1, nz = cz + c % 3 - 1;
+        if (!key_in_range(nx, ny, nz)) continue;
+        const uint32_t sl = dyn_find_slot(keys, mask, dyn_cell_key(nx, ny, nz));
+        if (sl == kNil) continue;
+        for (uint32_t j = head_v[sl]; j != kNil; j = next_v[j]) {
+            if (j >= i) continue;  // every pair once
+            const double4 q = in[j];
+            if (!dyn_near(x, y, z, __double2float_rn(q.x), __double2float_rn(q.y), __double2float_rn(q.z))) continue;
+            uint32_t a = i, b = j;
+            while (true) {
+                a = dyn_root(parent, a), b = dyn_root(parent, b);
+                if (a == b) break;
+                if (a < b) {
+                    const uint32_t t = a;
+                    a = b, b = t;
+                }
+                if (atomicCAS(parent + a, a, b) == a) break;  // hang the larger root under the smaller
+            }
+        }
+    }
+}
+
+// per vehicle point: final root, cluster size, landmark hits within 0.5 m (summed per cluster, as the reference's count_size)
+__global__ void dyn_count_kernel(const double4 *in, uint32_t n, const unsigned long long *keys, uint32_t mask, const uint32_t *head_l,
+                                 const uint32_t *next_l, uint32_t *parent, const uint32_t *cls, uint32_t *csize, uint32_t *clm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (cls[i] & 3u) != kClsVehicle) return;
+    const uint32_t r = dyn_root(parent, i);
+    const double4 p = in[i];
+    const float x = __double2float_rn(p.x), y = __double2float_rn(p.y), z = __double2float_rn(p.z);
+    const int cx = dyn_cell(x), cy = dyn_cell(y), cz = dyn_cell(z);
+    uint32_t hits = 0;
+    for (int c = 0; c < 27; ++c) {
+        const int nx = cx + c / 9 - 1, ny = cy + (c / 3) % 3 - 1, nz = cz + c % 3 - 1;
+        if (!key_in_range(nx, ny, nz)) continue;
+        const uint32_t sl = dyn_find_slot(keys, mask, dyn_cell_key(nx, ny, nz));
+        if (sl == kNil) continue;
+        for (uint32_t j = head_l[sl]; j != kNil; j = next_l[j]) {
+            const double4 q = in[j];
+            hits += dyn_near(x, y, z, __double2float_rn(q.x), __double2float_rn(q.y), __double2float_rn(q.z)) ? 1u : 0u;
+        }
+    }
+    atomicAdd(csize + r, 1u);
+    if (hits) atomicAdd(clm + r, hits);
+}
+
+// flags[i] = plain inlier, flags[n + i] = vehicle point of a kept cluster: one scan orders inliers first, vehicles after
+__global__ void dyn_flag_kernel(uint32_t n, const uint32_t *parent, const uint32_t *cls, const uint32_t *csize, const uint32_t *clm, double dy_th,
+                                uint32_t *flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cls[i] & 3u;
+    uint32_t keep_vehicle = 0;
+    if (c == kClsVehicle) {
+        const uint32_t r = dyn_root(parent, i);
+        const uint32_t size = csize[r];
+        // setMinClusterSize(5) (:137); is_static_vehicle iff count_size > int(dy_th * cluster_size) (:159)
+        keep_vehicle = (size >= 5u && (long long)clm[r] > (long long)__double2int_rz(__dmul_rn(dy_th, (double)size))) ? 1u : 0u;
+    }
+    flags[i] = c == kClsInlier ? 1u : 0u;
+    flags[n + i] = keep_vehicle;
+}
+
+__global__ void dyn_scatter_kernel(const double4 *in, uint32_t n, CropParams crop, const uint32_t *flags, const uint32_t *pos, double4 *out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * n || !flags[t]) return;
+    double4 p = in[t < n ? t : t - n];
+    crop_point(crop, p);  // re-applies the far-label zeroing
+    out[pos[t]] = p;
+}
+
 // one thread per point; fields may sit at any byte offset (the reference's message is a packed 17-byte record:
 // f32 x, y, z @0/4/8, u8 label @12, u32 rgb @13 — eval/kitti_pub.py:184-207), so they are assembled from bytes
 __device__ __forceinline__ float load_f32_unaligned(const uint8_t *p) {
@@ -340,6 +494,39 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
         for (size_t k = 0; k < group_order_[g].size(); ++k) perm_host[o++] = group_members_[g][group_order_[g][k]];
     SAGE_LAUNCH(ds_gather_kernel, fe_blocks(m), kFeThreads, 0, stream_, in, widx_.p, perm_host, crop, out, (uint32_t)m);
     return m;  // `out` is valid in stream order; callers that read it on the host synchronise themselves
+}
+
+size_t FrontEnd::preprocess_dynamic(const double4 *in, size_t n, const CropParams &crop, const DynFilterParams &dyn, double4 *out) {
+    SAGE_CUDA(cudaSetDevice(device_));
+    if (n == 0) return 0;
+    uint32_t cap = 1024;
+    while ((size_t)cap < 2 * n) cap *= 2;
+    if (cap > cell_cap_) {
+        cell_key_.ensure(cap);
+        cell_head_v_.ensure(cap);
+        cell_head_l_.ensure(cap);
+        cell_cap_ = cap;
+    }
+    next_v_.ensure(n), next_l_.ensure(n), parent_.ensure(n), csize_.ensure(n), clm_.ensure(n), cls_.ensure(n);
+    flags_.ensure(2 * n);
+    SAGE_CUDA(cudaMemsetAsync(cell_key_.p, 0xff, (size_t)cap * sizeof(unsigned long long), stream_));
+    SAGE_CUDA(cudaMemsetAsync(cell_head_v_.p, 0xff, (size_t)cap * sizeof(uint32_t), stream_));
+    SAGE_CUDA(cudaMemsetAsync(cell_head_l_.p, 0xff, (size_t)cap * sizeof(uint32_t), stream_));
+    SAGE_CUDA(cudaMemsetAsync(csize_.p, 0, n * sizeof(uint32_t), stream_));
+    SAGE_CUDA(cudaMemsetAsync(clm_.p, 0, n * sizeof(uint32_t), stream_));
+    SAGE_CUDA(cudaMemsetAsync(total_.p, 0, 2 * sizeof(uint32_t), stream_));
+    const uint32_t nn = (uint32_t)n;
+    SAGE_LAUNCH(dyn_classify_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, crop, dyn, cell_key_.p, cap - 1, cell_head_v_.p, cell_head_l_.p,
+                next_v_.p, next_l_.p, parent_.p, cls_.p, total_.p + 1);
+    SAGE_LAUNCH(dyn_union_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, cell_key_.p, cap - 1, cell_head_v_.p, next_v_.p, parent_.p, cls_.p);
+    SAGE_LAUNCH(dyn_count_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, cell_key_.p, cap - 1, cell_head_l_.p, next_l_.p, parent_.p, cls_.p,
+                csize_.p, clm_.p);
+    SAGE_LAUNCH(dyn_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, nn, parent_.p, cls_.p, csize_.p, clm_.p, dyn.dy_th, flags_.p);
+    scan_flags(2 * n, total_pin_.p, total_.p + 1);
+    SAGE_LAUNCH(dyn_scatter_kernel, fe_blocks(2 * n), kFeThreads, 0, stream_, in, nn, crop, flags_.p, pos_.p, out);
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    if (total_pin_.p[1]) throw ArgError("Preprocess: point outside the +-2^20 cell range of the dynamic-vehicle filter");
+    return total_pin_.p[0];
 }
 
 void FrontEnd::unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,

@@ -19,6 +19,14 @@ struct GroupTable {  // passed to kernels by value
     double voxel_size[kMaxGroups];
 };
 
+struct DynFilterParams {  // Preprocess' dynamic-vehicle branch (core/Preprocessing.cpp:95-172)
+    int n_dynamic;
+    int dynamic_labels[32];  // voxel_labels[dynamic_vehicle_voxid]
+    int n_landmark;
+    int landmark_labels[32];  // dynamic_remove_lankmark
+    double dy_th;             // dynamic_vehicle_filter_th
+};
+
 struct CropParams {
     int enabled;
     double max_range, min_range, label_max_range;
@@ -37,6 +45,10 @@ public:
     size_t downsample(const double4 *in, size_t n, double vox_scale, const CropParams &crop, double4 *out);
     // Preprocess only (order-preserving compaction).  Returns kept count.  Synchronises.
     size_t preprocess(const double4 *in, size_t n, const CropParams &crop, double4 *out);
+    // Preprocess with dynamic_vehicle_filter = true: range crop, then vehicle-labelled points survive only in clusters
+    // (0.5 m single linkage, >= 5 points) that touch enough landmark-labelled points.  Non-vehicle inliers first (input
+    // order), kept vehicle points after them (input order).  Returns the kept count.  Synchronises.
+    size_t preprocess_dynamic(const double4 *in, size_t n, const CropParams &crop, const DynFilterParams &dyn, double4 *out);
     // utils::PointCloud2ToEigen (ros/ros2/Utils.hpp:161-180) on the device: packed records -> x, y, z, label as f64
     void unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,
                             uint32_t label_off, int label_is_f32, double4 *out);
@@ -54,6 +66,10 @@ private:
     uint32_t tcap_ = 0;
     DevBuf<uint32_t> slot_, flags_, pos_, block_sums_, widx_, whash_, perm_;
     DevBuf<uint32_t> total_;
+    // dynamic-vehicle filter scratch
+    DevBuf<unsigned long long> cell_key_;
+    DevBuf<uint32_t> cell_head_v_, cell_head_l_, next_v_, next_l_, parent_, csize_, clm_, cls_;
+    uint32_t cell_cap_ = 0;
     PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_[2];
     int parity_ = 0;
     std::vector<std::vector<uint32_t>> group_members_, group_hashes_, group_order_;

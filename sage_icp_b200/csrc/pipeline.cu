@@ -35,8 +35,16 @@ Pipeline::Pipeline(const sage_config_pod &c, int device)
     // the reference evaluates voxel_labels[dynamic_vehicle_voxid] unconditionally (pipeline/sageICP.cpp:63): out of range
     // there is UB, here it is an error
     if (c.dynamic_vehicle_voxid < 0 || c.dynamic_vehicle_voxid >= c.n_groups) throw ArgError("dynamic_vehicle_voxid out of range");
-    if (c.dynamic_vehicle_filter)
-        throw ArgError("dynamic_vehicle_filter=true is not implemented (PCL clustering branch, core/Preprocessing.cpp:95-172)");
+    {  // dynamic-vehicle branch of Preprocess: labels of the vehicle voxel group and the landmark labels (pipeline/sageICP.cpp:61-64)
+        const int g = c.dynamic_vehicle_voxid;
+        const int n_dyn = c.group_offsets[g + 1] - c.group_offsets[g];
+        if (n_dyn > 32 || c.n_dynamic_remove_lankmark > 32) throw ArgError("at most 32 dynamic / landmark labels supported");
+        dyn_.n_dynamic = n_dyn;
+        for (int k = 0; k < n_dyn; ++k) dyn_.dynamic_labels[k] = c.group_labels[c.group_offsets[g] + k];
+        dyn_.n_landmark = c.n_dynamic_remove_lankmark;
+        for (int k = 0; k < c.n_dynamic_remove_lankmark; ++k) dyn_.landmark_labels[k] = c.dynamic_remove_lankmark[k];
+        dyn_.dy_th = c.dynamic_vehicle_filter_th;
+    }
     // own copies of the label arrays (the POD's pointers belong to the caller)
     cfg_.group_offsets = cfg_.group_labels = cfg_.basic_parts_labels = cfg_.dynamic_remove_lankmark = nullptr;
     cfg_.voxel_size = nullptr;
@@ -143,7 +151,13 @@ void Pipeline::register_frame_dev(const double4 *raw, size_t n, const double *ti
         raw = deskewed_.p;
     }
     const auto t0 = clock::now();
-    voxelize_dev(raw, n, crop());  // Preprocess fused into the first downsample pass
+    if (cfg_.dynamic_vehicle_filter) {  // Preprocess with the vehicle filter, then Voxelize
+        filtered_.ensure(n ? n : 1);
+        const size_t nf = preprocess_dev(raw, n, filtered_.p);
+        voxelize_dev(filtered_.p, nf, CropParams{0, 0, 0, 0});
+    } else {
+        voxelize_dev(raw, n, crop());  // Preprocess (range branch) fused into the first downsample pass
+    }
     const double sigma = get_adaptive_threshold();
     const Pose prediction = get_prediction_model();
     const Pose last_pose = !poses_.empty() ? poses_.back() : pose_identity();
@@ -161,10 +175,14 @@ void Pipeline::register_frame_dev(const double4 *raw, size_t n, const double *ti
     t_all = std::chrono::duration<double>(t2 - t0).count();
 }
 
+size_t Pipeline::preprocess_dev(const double4 *raw, size_t n, double4 *out) {
+    return cfg_.dynamic_vehicle_filter ? fe_.preprocess_dynamic(raw, n, crop(), dyn_, out) : fe_.preprocess(raw, n, crop(), out);
+}
+
 long long Pipeline::preprocess_host(const double *xyzl, size_t n, std::vector<double> &out) {
     double4 *raw = map_.stage_points(xyzl, n);
     tmp_.ensure(n ? n : 1);
-    const size_t m = fe_.preprocess(raw, n, crop(), tmp_.p);
+    const size_t m = preprocess_dev(raw, n, tmp_.p);
     fetch(tmp_.p, m, out);
     return (long long)m;
 }

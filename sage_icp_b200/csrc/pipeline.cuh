@@ -41,6 +41,8 @@ private:
     double compute_threshold();
     void reset_threshold();
     CropParams crop() const;
+    size_t preprocess_dev(const double4 *raw, size_t n, double4 *out);  // Preprocess, either branch
+    DynFilterParams dyn_{};
 
     sage_config_pod cfg_;  // scalar fields only (array pointers nulled)
     VoxelMapGPU map_;
@@ -51,7 +53,7 @@ private:
     int num_samples_ = 0;
     Pose model_deviation_ = pose_identity();
 
-    DevBuf<double4> ds_, src_, tmp_, deskewed_;
+    DevBuf<double4> ds_, src_, tmp_, deskewed_, filtered_;
     DevBuf<double> ts_;
     DevBuf<uint8_t> packed_;
     DevBuf<double4> unpacked_;

@@ -104,7 +104,48 @@ def test_bad_config_fails_loudly(cfg):
     with pytest.raises(sg.SageError):
         sg.SagePipeline(SageConfig())  # empty voxel_labels: UB in the reference, error here
     with pytest.raises(sg.SageError):
-        sg.SagePipeline(launch_config(dynamic_vehicle_filter=True))
+        sg.SagePipeline(launch_config(dynamic_vehicle_voxid=9))  # voxel_labels[9]: out of range (UB in the reference)
+
+
+@pytest.mark.parametrize("dy_th,seed", [(0.5, 3), (0.05, 4), (3.0, 5)])
+def test_dynamic_vehicle_filter_preprocess(orc, dy_th, seed):
+    """Preprocess with dynamic_vehicle_filter = true (core/Preprocessing.cpp:95-172): same kept points in the same order as the
+    oracle's restatement of the PCL clustering + landmark test (the order of the re-admitted vehicle points is input order on
+    both sides; PCL's own cluster order is not reproducible here — DESIGN.md section 6)."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config(dynamic_vehicle_filter=True, dynamic_vehicle_filter_th=dy_th)
+    p = sg.SagePipeline(cfg)
+    scan = _scan(seed, beams=48, az=1000)
+    out = p.preprocess(scan)
+    ref = orc.preprocess_dynamic(cfg, scan)
+    assert out.shape == ref.shape and np.array_equal(out, ref)
+    plain = orc.preprocess(scan, cfg.max_range, cfg.min_range, cfg.label_max_range)
+    veh = [10, 11, 13, 15, 16, 18, 20]
+    n_in, n_out = np.isin(plain[:, 3], veh).sum(), np.isin(out[:, 3], veh).sum()
+    assert n_in > 500 and n_out <= n_in
+    if dy_th == 0.5:
+        assert 0 < n_out < n_in  # some clusters stay (next to sidewalk / parking points), some go
+    # non-vehicle points are untouched and come first, in input order
+    keep = ~np.isin(plain[:, 3], veh)
+    assert np.array_equal(out[: keep.sum()], plain[keep])
+
+
+def test_register_frame_with_dynamic_vehicle_filter(orc):
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config(dynamic_vehicle_filter=True)  # ros/launch/odometry.launch.py:50
+    gp, op = sg.SagePipeline(cfg), orc.OraclePipeline(cfg, evict_faithful=False)
+    traj = syn.trajectory(6)
+    for i in range(6):
+        scan = syn.make_scan(700 + i, tuple(traj[i]), n_beams=32, n_az=800)
+        pg, _, _ = gp.register_frame(scan)
+        po, _, _ = op.register_frame(scan)
+        dt, da = pose_delta(pg, po)
+        assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (i, dt, da)
+        assert np.array_equal(gp.last_source(), op.last_source()), i
+        assert np.array_equal(gp.last_frame_downsample(), op.last_frame_downsample()), i
 
 
 def _pointcloud2_buffer(scan, label_f32=False):

@@ -21,12 +21,13 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=40)
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--az", type=int, default=1875)
+    ap.add_argument("--dynamic-filter", action="store_true", help="dynamic_vehicle_filter = true (ros/launch/odometry.launch.py:50)")
     a = ap.parse_args()
     import torch
     import sage_icp_b200 as sg
     from sage_icp_b200 import synthetic as syn
     from oracle import oracle_py as orc
-    cfg = sg.launch_config()
+    cfg = sg.launch_config(dynamic_vehicle_filter=a.dynamic_filter)
     traj = syn.trajectory(a.frames)
     gp = sg.SagePipeline(cfg)
     op = orc.OraclePipeline(cfg, threads=orc.max_threads(), evict_faithful=False)
@@ -54,7 +55,7 @@ def main():
     g, c = np.array(t_gpu[warm:]), np.array(t_cpu[warm:])
     print(json.dumps({
         "workload": "BASELINE configs[2]: streaming RegisterFrame, synthetic KITTI-shaped drive, incremental Update on device",
-        "frames": a.frames, "rays_per_scan": a.beams * a.az, "gpu_frames_per_s": float(1.0 / g.mean()), "gpu_ms_per_frame_median": float(1e3 * np.median(g)),
+        "frames": a.frames, "dynamic_vehicle_filter": bool(a.dynamic_filter), "rays_per_scan": a.beams * a.az, "gpu_frames_per_s": float(1.0 / g.mean()), "gpu_ms_per_frame_median": float(1e3 * np.median(g)),
         "gpu_ms_per_frame_p99": float(1e3 * np.percentile(g, 99)), "mean_gn_iterations": float(np.mean(iters)),
         "mean_t_icp_ms": float(1e3 * np.mean(t_icps[warm:])), "mean_t_all_ms (front end + icp, reference meaning)": float(1e3 * np.mean(t_alls[warm:])), "mean_queries": float(np.mean(nsrc)),
         "map_voxels_end": gp.map().num_voxels(), "map_points_end": gp.map().num_points(), "gpu_launches_per_frame": (sg.launch_count() - l0) / a.frames,

@@ -253,6 +253,24 @@ __device__ __forceinline__ uint32_t dyn_find_slot(const unsigned long long *keys
 }
 
 // classify + put vehicle / landmark points on their cell's list
+// Vehicle points go on a FINE grid (0.288 m cells: any two points of one cell are closer than 0.288 * sqrt(3) = 0.4988 m, i.e.
+// connected by definition), landmark points on a 0.5 m grid (the radius of the hit count).  Both grids share one key table;
+// bit 63 of the key tells them apart.
+constexpr float kFineInv = 1.0f / 0.288f;
+__device__ __forceinline__ int dyn_fine_cell(float v) { return __float2int_rd(__fmul_rn(v, kFineInv)); }
+__device__ __forceinline__ uint32_t dyn_insert_slot(unsigned long long *keys, uint32_t mask, unsigned long long key) {
+    uint32_t sl = (uint32_t)mix64(key) & mask;
+    while (true) {
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(keys + sl);
+        if (cur == key) return sl;
+        if (cur == kEmptyKey) {
+            const unsigned long long old = atomicCAS(keys + sl, kEmptyKey, key);
+            if (old == kEmptyKey || old == key) return sl;
+        }
+        sl = (sl + 1) & mask;
+    }
+}
+
 __global__ void dyn_classify_kernel(const double4 *in, uint32_t n, CropParams crop, DynFilterParams dp, unsigned long long *keys, uint32_t mask,
                                     uint32_t *head_v, uint32_t *head_l, uint32_t *next_v, uint32_t *next_l, uint32_t *parent, uint32_t *cls,
                                     uint32_t *err) {
@@ -272,24 +290,20 @@ __global__ void dyn_classify_kernel(const double4 *in, uint32_t n, CropParams cr
     cls[i] = (vehicle ? kClsVehicle : kClsInlier) | (landmark ? kClsLandmarkBit : 0u);
     if (!vehicle && !landmark) return;
     const float x = __double2float_rn(p.x), y = __double2float_rn(p.y), z = __double2float_rn(p.z);
+    const int fx = dyn_fine_cell(x), fy = dyn_fine_cell(y), fz = dyn_fine_cell(z);
     const int cx = dyn_cell(x), cy = dyn_cell(y), cz = dyn_cell(z);
-    if (!key_in_range(cx, cy, cz)) {
+    if (!key_in_range(fx, fy, fz) || !key_in_range(cx, cy, cz)) {
         atomicAdd(err, 1u);
         return;
     }
-    const unsigned long long key = dyn_cell_key(cx, cy, cz);
-    uint32_t sl = (uint32_t)mix64(key) & mask;
-    while (true) {
-        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(keys + sl);
-        if (cur == key) break;
-        if (cur == kEmptyKey) {
-            const unsigned long long old = atomicCAS(keys + sl, kEmptyKey, key);
-            if (old == kEmptyKey || old == key) break;
-        }
-        sl = (sl + 1) & mask;
+    if (vehicle) {
+        const uint32_t sl = dyn_insert_slot(keys, mask, dyn_cell_key(fx, fy, fz) | (1ull << 63));
+        next_v[i] = atomicExch(head_v + sl, i);
     }
-    if (vehicle) next_v[i] = atomicExch(head_v + sl, i);
-    if (landmark) next_l[i] = atomicExch(head_l + sl, i);
+    if (landmark) {
+        const uint32_t sl = dyn_insert_slot(keys, mask, dyn_cell_key(cx, cy, cz));
+        next_l[i] = atomicExch(head_l + sl, i);
+    }
 }
 
 __device__ __forceinline__ uint32_t dyn_root(const uint32_t *parent, uint32_t a) {
@@ -300,43 +314,66 @@ __device__ __forceinline__ uint32_t dyn_root(const uint32_t *parent, uint32_t a)
     }
 }
 
-// union every pair of vehicle points closer than 0.5 m; the smaller index becomes the root
+__device__ __forceinline__ void dyn_unite(uint32_t *parent, uint32_t a, uint32_t b) {
+    while (true) {
+        a = dyn_root(parent, a), b = dyn_root(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const uint32_t t = a;
+            a = b, b = t;
+        }
+        if (atomicCAS(parent + a, a, b) == a) return;  // hang the larger root under the smaller: roots end as minimum indices
+    }
+}
+
+// Single-linkage clusters of the vehicle points (= PCL's EuclideanClusterExtraction with tolerance 0.5).  A point joins its own
+// fine cell (all of it is within 0.5 m), then for each of the 124 fine cells that can hold a point within 0.5 m it looks for ONE
+// such point — cell mates of that point are already tied to it — and skips cells that already belong to its component.
 __global__ void dyn_union_kernel(const double4 *in, uint32_t n, const unsigned long long *keys, uint32_t mask, const uint32_t *head_v,
                                  const uint32_t *next_v, uint32_t *parent, const uint32_t *cls) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (cls[i] & 3u) != kClsVehicle) return;
     const double4 p = in[i];
     const float x = __double2float_rn(p.x), y = __double2float_rn(p.y), z = __double2float_rn(p.z);
-    const int cx = dyn_cell(x), cy = dyn_cell(y), cz = dyn_cell(z);
-    for (int c = 0; c < 27; ++c) {
-        const int nx = cx + c / 9 - 1, ny = cy + (c / 3) % 3 - 1, nz = cz + c % 3 - 1;
+    const int fx = dyn_fine_cell(x), fy = dyn_fine_cell(y), fz = dyn_fine_cell(z);
+    for (int c = 0; c < 125; ++c) {
+        const int nx = fx + c / 25 - 2, ny = fy + (c / 5) % 5 - 2, nz = fz + c % 5 - 2;
         if (!key_in_range(nx, ny, nz)) continue;
-        const uint32_t sl = dyn_find_slot(keys, mask, dyn_cell_key(nx, ny, nz));
+        const uint32_t sl = dyn_find_slot(keys, mask, dyn_cell_key(nx, ny, nz) | (1ull << 63));
         if (sl == kNil) continue;
-        for (uint32_t j = head_v[sl]; j != kNil; j = next_v[j]) {
-            if (j >= i) continue;  // every pair once
+        const uint32_t first = head_v[sl];
+        if (c == 62) {  // own cell
+            if (first != i) dyn_unite(parent, i, first);
+            continue;
+        }
+        if (dyn_root(parent, first) == dyn_root(parent, i)) continue;  // already one component (cell mates share a root eventually)
+        for (uint32_t j = first; j != kNil; j = next_v[j]) {
             const double4 q = in[j];
-            if (!dyn_near(x, y, z, __double2float_rn(q.x), __double2float_rn(q.y), __double2float_rn(q.z))) continue;
-            uint32_t a = i, b = j;
-            while (true) {
-                a = dyn_root(parent, a), b = dyn_root(parent, b);
-                if (a == b) break;
-                if (a < b) {
-                    const uint32_t t = a;
-                    a = b, b = t;
-                }
-                if (atomicCAS(parent + a, a, b) == a) break;  // hang the larger root under the smaller
+            if (dyn_near(x, y, z, __double2float_rn(q.x), __double2float_rn(q.y), __double2float_rn(q.z))) {
+                dyn_unite(parent, i, j);
+                break;
             }
         }
     }
 }
 
+// cluster sizes
+__global__ void dyn_size_kernel(uint32_t n, const uint32_t *parent, const uint32_t *cls, uint32_t *csize) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || (cls[i] & 3u) != kClsVehicle) return;
+    atomicAdd(csize + dyn_root(parent, i), 1u);
+}
+
 // per vehicle point: final root, cluster size, landmark hits within 0.5 m (summed per cluster, as the reference's count_size)
 __global__ void dyn_count_kernel(const double4 *in, uint32_t n, const unsigned long long *keys, uint32_t mask, const uint32_t *head_l,
-                                 const uint32_t *next_l, uint32_t *parent, const uint32_t *cls, uint32_t *csize, uint32_t *clm) {
+                                 const uint32_t *next_l, uint32_t *parent, const uint32_t *cls, const uint32_t *csize, uint32_t *clm, double dy_th) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || (cls[i] & 3u) != kClsVehicle) return;
     const uint32_t r = dyn_root(parent, i);
+    // the verdict is "hits > int(dy_th * size)" (:159): clusters too small to be kept, or already over the bar, need no more counting
+    // (the reference breaks out of its loops the same way)
+    const uint32_t size = csize[r];
+    if (size < 5u || (long long)*reinterpret_cast<volatile uint32_t *>(clm + r) > (long long)__double2int_rz(__dmul_rn(dy_th, (double)size))) return;
     const double4 p = in[i];
     const float x = __double2float_rn(p.x), y = __double2float_rn(p.y), z = __double2float_rn(p.z);
     const int cx = dyn_cell(x), cy = dyn_cell(y), cz = dyn_cell(z);
@@ -351,7 +388,6 @@ __global__ void dyn_count_kernel(const double4 *in, uint32_t n, const unsigned l
             hits += dyn_near(x, y, z, __double2float_rn(q.x), __double2float_rn(q.y), __double2float_rn(q.z)) ? 1u : 0u;
         }
     }
-    atomicAdd(csize + r, 1u);
     if (hits) atomicAdd(clm + r, hits);
 }
 
@@ -500,7 +536,7 @@ size_t FrontEnd::preprocess_dynamic(const double4 *in, size_t n, const CropParam
     SAGE_CUDA(cudaSetDevice(device_));
     if (n == 0) return 0;
     uint32_t cap = 1024;
-    while ((size_t)cap < 2 * n) cap *= 2;
+    while ((size_t)cap < 4 * n) cap *= 2;  // two grids share the table
     if (cap > cell_cap_) {
         cell_key_.ensure(cap);
         cell_head_v_.ensure(cap);
@@ -519,8 +555,9 @@ size_t FrontEnd::preprocess_dynamic(const double4 *in, size_t n, const CropParam
     SAGE_LAUNCH(dyn_classify_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, crop, dyn, cell_key_.p, cap - 1, cell_head_v_.p, cell_head_l_.p,
                 next_v_.p, next_l_.p, parent_.p, cls_.p, total_.p + 1);
     SAGE_LAUNCH(dyn_union_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, cell_key_.p, cap - 1, cell_head_v_.p, next_v_.p, parent_.p, cls_.p);
+    SAGE_LAUNCH(dyn_size_kernel, fe_blocks(n), kFeThreads, 0, stream_, nn, parent_.p, cls_.p, csize_.p);
     SAGE_LAUNCH(dyn_count_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, cell_key_.p, cap - 1, cell_head_l_.p, next_l_.p, parent_.p, cls_.p,
-                csize_.p, clm_.p);
+                csize_.p, clm_.p, dyn.dy_th);
     SAGE_LAUNCH(dyn_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, nn, parent_.p, cls_.p, csize_.p, clm_.p, dyn.dy_th, flags_.p);
     scan_flags(2 * n, total_pin_.p, total_.p + 1);
     SAGE_LAUNCH(dyn_scatter_kernel, fe_blocks(2 * n), kFeThreads, 0, stream_, in, nn, crop, flags_.p, pos_.p, out);

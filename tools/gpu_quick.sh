@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout=400 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
-timeout 600 python tools/stream_bench.py --frames 300 --cpu-frames 20 > gpurun_out/stream.json 2> gpurun_out/stream.err; echo rc=$?; cat gpurun_out/stream.json; tail -3 gpurun_out/stream.err
+timeout 600 python -m pytest tests/test_gpu_pipeline.py -m gpu -q --timeout=200 --timeout-method=thread 2>&1 | tail -4
+timeout 600 python tools/stream_bench.py --frames 200 --cpu-frames 6 --dynamic-filter > gpurun_out/stream_dyn.json 2> gpurun_out/stream_dyn.err; echo rc=$?; cat gpurun_out/stream_dyn.json; tail -3 gpurun_out/stream_dyn.err

@@ -134,9 +134,10 @@ def emit(text: str):
 
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+    except (OSError, KeyError, ValueError, TypeError):
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s; MEASURED_PEAKS.json absent or without hbm_gbs)"
 
 
 def run_reference(args):

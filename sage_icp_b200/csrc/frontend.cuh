@@ -64,7 +64,7 @@ private:
     DevBuf<unsigned long long> tkey_;
     DevBuf<uint32_t> tfirst_;
     uint32_t tcap_ = 0;
-    DevBuf<uint32_t> slot_, flags_, pos_, block_sums_, widx_, whash_, perm_;
+    DevBuf<uint32_t> slot_, flags_, pos_, block_sums_, widx_;
     DevBuf<uint32_t> total_;
     // dynamic-vehicle filter scratch
     DevBuf<unsigned long long> cell_key_;

@@ -309,8 +309,15 @@ __device__ __forceinline__ bool accept_pair(const double4 &nb, double sx, double
 // Warp-cooperative f32 search of one query over all 27 voxels: lane = voxel in the reference's enumeration order (all 27
 // probed at once), found voxels scanned four at a time by the whole warp, same ranking + error band; ambiguous queries
 // fall through to nn_exact<32>.  Returns the winner's record index or kNil, identical on every lane.
+// What the thread-per-query phase hands over with a deferred query: the best two metrics and the winner so far, and which of
+// the 27 voxels it has already scanned.  {INF, INF, kNil, 0} = nothing done yet (small-scan mode).
+struct Carried {
+    float min1, min2;
+    uint32_t idx1, visited;
+};
+
 template <bool COUNT>
-__device__ __noinline__ uint32_t search_query_warp(const IterParams &p, int lane, const double4 s, unsigned long long &n_scanned,
+__device__ __noinline__ uint32_t search_query_warp(const IterParams &p, int lane, const double4 s, const Carried cs, unsigned long long &n_scanned,
                                                    unsigned long long &n_probes, unsigned long long &n_exact) {
     const double vs = p.voxel_size;
     const float vs32 = p.vs32, th32 = p.th32;
@@ -322,16 +329,27 @@ __device__ __noinline__ uint32_t search_query_warp(const IterParams &p, int lane
     bool odd = !p.fast_ok || (qlf != qlf) || !(fabsf(bx) <= 2.0f * vs32 && fabsf(by) <= 2.0f * vs32 && fabsf(bz) <= 2.0f * vs32);
     uint32_t widx = kNil;
     if (!odd) {
+        // lane = voxel in the reference's enumeration order.  Skip what the first phase scanned and what its best-so-far
+        // already rules out (same bound as there: lower bound of the metric over the voxel's box > best + 2 e).
+        const int ox = lane / 9 - 1, oy = (lane / 3) % 3 - 1, oz = lane % 3 - 1;
         bool found = false;
         uint32_t blk = 0, cnt = 0;
-        if (lane < 27) {
-            const int nx = kx + lane / 9 - 1, ny = ky + (lane / 3) % 3 - 1, nz = kz + lane % 3 - 1;
-            if (key_in_range(nx, ny, nz)) found = tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), blk, cnt) && cnt > 0;
+        if (lane < 27 && !((cs.visited >> lane) & 1u)) {
+            float sxm, sxp, sym, syp, szm, szp;
+            axis_bounds(bx, kx, vs32, p.box_margin, p.smin32, sxm, sxp);
+            axis_bounds(by, ky, vs32, p.box_margin, p.smin32, sym, syp);
+            axis_bounds(bz, kz, vs32, p.box_margin, p.smin32, szm, szp);
+            const float lb = (ox < 0 ? sxm : (ox > 0 ? sxp : 0.0f)) + (oy < 0 ? sym : (oy > 0 ? syp : 0.0f)) + (oz < 0 ? szm : (oz > 0 ? szp : 0.0f));
+            const int nx = kx + ox, ny = ky + oy, nz = kz + oz;
+            if (lb <= prune_bound(p, cs.min1) && key_in_range(nx, ny, nz)) {
+                found = tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), blk, cnt) && cnt > 0;
+                if (COUNT) n_probes += 1;
+            }
         }
         unsigned fm = __ballot_sync(FULL, found);
-        if (COUNT && lane == 0) n_probes += 27;
-        float min1 = INF, min2 = INF;
-        uint32_t idx1 = kNil;
+        // lane 0 carries the first phase's result into the reduction
+        float min1 = lane == 0 ? cs.min1 : INF, min2 = lane == 0 ? cs.min2 : INF;
+        uint32_t idx1 = lane == 0 ? cs.idx1 : kNil;
         while (fm) {  // four voxels per round: their loads are independent
             int l[4];
             uint32_t b[4], c[4];
@@ -377,6 +395,24 @@ __device__ __noinline__ uint32_t search_query_warp(const IterParams &p, int lane
     return widx;
 }
 
+// Acceptance, residual and sums of up to 32 warp-searched queries at once: lane k holds the k-th query of the batch.
+template <int COLS>
+__device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s_acc)[COLS], uint32_t q, uint32_t widx, bool have) {
+    if (!have) return;
+    double4 nb = make_double4(0, 0, 0, 0);
+    bool ok = false;
+    if (widx != kNil) {
+        const double4 s = ld256(p.src + q);
+        nb = ldg256(p.blk_pts + widx);
+        ok = accept_pair(nb, s.x, s.y, s.z, p.max_dist);
+        if (ok) accumulate_pair(s_acc, threadIdx.x, p.kern, s.x, s.y, s.z, nb.x, nb.y, nb.z);
+    }
+    if (p.tgt_out) {
+        st256(p.tgt_out + q, nb);
+        p.matched_out[q] = ok ? 1 : 0;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The search kernel: one launch per Gauss-Newton iteration.
 // Light phase — one thread per query: home voxel, then neighbours nearest-bounding-box first with the prune bound
@@ -394,6 +430,7 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
     __shared__ Pose s_est;
     __shared__ uint32_t s_cnt[kWarps];
     __shared__ uint32_t s_list[kNnThreads];
+    __shared__ Carried s_carry[kNnThreads];
     __shared__ double s_norm;
     __shared__ int s_last;
     IcpState *st = p.st;
@@ -412,6 +449,9 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
 
     if (p.all_warp) {
         // small scans (pipeline level: a few thousand queries): give every query a whole warp straight away
+        uint32_t bq = 0, bw = kNil;  // lane k keeps the k-th query this warp searched since the last flush
+        bool bhave = false;
+        int fill = 0;
         for (uint32_t q = blockIdx.x * kWarps + warp; q < p.n; q += gridDim.x * kWarps) {
             double4 s = ld256(p.src + q);
             if (p.apply_est) {  // source <- est * source, in place (core/Registration.cpp:133); every lane computes the same
@@ -421,22 +461,17 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
                 s.x = x, s.y = y, s.z = z;
                 if (lane == 0) st256(p.src + q, s);
             }
-            const uint32_t w = search_query_warp<COUNT>(p, lane, s, n_scanned, n_probes, n_exact);
-            if (lane == 0) {
-                double4 nb = make_double4(0, 0, 0, 0);
-                bool ok = false;
-                if (w != kNil) {
-                    nb = ldg256(p.blk_pts + w);
-                    ok = accept_pair(nb, s.x, s.y, s.z, p.max_dist);
-                    if (ok) accumulate_pair(s_acc, threadIdx.x, p.kern, s.x, s.y, s.z, nb.x, nb.y, nb.z);
-                }
-                if (p.tgt_out) {
-                    st256(p.tgt_out + q, nb);
-                    p.matched_out[q] = ok ? 1 : 0;
-                }
-                if (COUNT) n_heavy += 1;
+            const uint32_t w = search_query_warp<COUNT>(p, lane, s, Carried{INF, INF, kNil, 0u}, n_scanned, n_probes, n_exact);
+            if (lane == fill) bq = q, bw = w, bhave = true;
+            if (COUNT && lane == 0) n_heavy += 1;
+            if (++fill == 32) {
+                __syncwarp();  // lane 0's stores of the transformed points are visible to the lanes that flush them
+                flush_warp_batch(p, s_acc, bq, bw, bhave);
+                bhave = false, fill = 0;
             }
         }
+        __syncwarp();
+        flush_warp_batch(p, s_acc, bq, bw, bhave);
     }
     const uint32_t n_chunks = p.all_warp ? 0u : (p.n + 31) / 32, chunks_per_pass = gridDim.x * kWarps;
     const uint32_t passes = (n_chunks + chunks_per_pass - 1) / chunks_per_pass;  // same for every warp of every block
@@ -470,7 +505,7 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
         SAGE_STAMP(4);
 
         float min1 = INF, min2 = INF;
-        uint32_t idx1 = kNil;
+        uint32_t idx1 = kNil, visited_bits = 0;
         uint32_t hblk = 0, hcnt = 0;
         const bool hfound = valid && !odd && key_in_range(kx, ky, kz) && tbl_find(p.tbl, p.mask, pack_key(kx, ky, kz), hblk, hcnt) && hcnt > 0;
         SAGE_STAMP(5);
@@ -512,6 +547,7 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
                 if (nn < 0 || !(best_lb <= bound)) break;
                 if (budget-- <= 0) {
                     heavy = true;
+                    visited_bits = visited;
                     break;
                 }
                 visited |= 1u << nn;
@@ -577,27 +613,30 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
             before += w < warp ? s_cnt[w] : 0u;
             total += s_cnt[w];
         }
-        if (heavy) s_list[before + __popc(hm & ((1u << lane) - 1u))] = q;
+        if (heavy) {
+            const uint32_t slot = before + __popc(hm & ((1u << lane) - 1u));
+            s_list[slot] = q;
+            // a query that met a record the f32 ranking cannot serve (`odd`) starts over in the warp phase, which will meet it again
+            s_carry[slot] = odd ? Carried{INF, INF, kNil, 0u} : Carried{min1, min2, idx1, visited_bits};
+        }
         __syncthreads();
         if (p.dbg && threadIdx.x == 0 && pass == 0) p.dbg[kDbg * blockIdx.x + 2] = gtime();  // whole block done with the light phase
-        for (uint32_t i = warp; i < total; i += kWarps) {
-            const uint32_t hq = s_list[i];
-            const double4 s = ld256(p.src + hq);  // transformed above (same block, ordered by the barrier)
-            const uint32_t w = search_query_warp<COUNT>(p, lane, s, n_scanned, n_probes, n_exact);
-            if (lane == 0) {
-                double4 nb = make_double4(0, 0, 0, 0);
-                bool ok = false;
-                if (w != kNil) {
-                    nb = ldg256(p.blk_pts + w);
-                    ok = accept_pair(nb, s.x, s.y, s.z, p.max_dist);
-                    if (ok) accumulate_pair(s_acc, threadIdx.x, p.kern, s.x, s.y, s.z, nb.x, nb.y, nb.z);
+        {
+            uint32_t bq = 0, bw = kNil;
+            bool bhave = false;
+            int fill = 0;
+            for (uint32_t i = warp; i < total; i += kWarps) {
+                const uint32_t hq = s_list[i];
+                const double4 s = ld256(p.src + hq);  // transformed above (same block, ordered by the barrier)
+                const uint32_t w = search_query_warp<COUNT>(p, lane, s, s_carry[i], n_scanned, n_probes, n_exact);
+                if (lane == fill) bq = hq, bw = w, bhave = true;
+                if (COUNT && lane == 0) n_heavy += 1;
+                if (++fill == 32) {
+                    flush_warp_batch(p, s_acc, bq, bw, bhave);
+                    bhave = false, fill = 0;
                 }
-                if (p.tgt_out) {
-                    st256(p.tgt_out + hq, nb);
-                    p.matched_out[hq] = ok ? 1 : 0;
-                }
-                if (COUNT) n_heavy += 1;
             }
+            flush_warp_batch(p, s_acc, bq, bw, bhave);
         }
         if (pass + 1 < passes) __syncthreads();  // s_cnt / s_list are reused by the next pass
     }

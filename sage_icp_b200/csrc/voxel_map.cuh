@@ -122,6 +122,7 @@ private:
     PinBuf<IcpState> icp_pin_;
     DevBuf<double> partials_;
     int nn_grid_ = 0;
+    size_t all_warp_max_ = 0;  // scans up to this many queries use the warp-per-query mode
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
     int light_probes_ = 8;  // neighbour probes per query in the thread-per-query phase before the query is deferred
     bool dbg_on_ = false;

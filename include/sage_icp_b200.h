@@ -189,6 +189,12 @@ int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms);
 /* Total kernel launches issued by this library in the calling process since load (bench.py's gpu_launches). */
 int64_t sage_launch_count(void);
 
+/* Host utility behind sage_voxel_downsample: iteration order of the reference's unreserved tsl::robin_map<Voxel, ...> (v1.0.1)
+ * after `n` DISTINCT keys with the given 20-bit VoxelHash values (core/Preprocessing.cpp:35-40) were inserted in this
+ * order — core/Preprocessing.cpp:76-82 emits the down-sampled cloud in that order.  order_out[j] = input position of the
+ * j-th element.  Pure host code (no device needed); exported so that it can be tested on its own. */
+int sage_robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out);
+
 /* Query shard owned by `rank` out of `world` for n queries: contiguous [begin, end).  Pure host arithmetic. */
 int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end);
 /* NCCL plumbing for the sharded ICP: rank 0 calls sage_nccl_unique_id and ships the 128 bytes to its

@@ -107,6 +107,16 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return int(b.value), int(e.value)
 
 
+def robin_iteration_order(hash20) -> np.ndarray:
+    """Host utility of the down-sampler: tsl::robin_map iteration order for distinct keys with these 20-bit hashes."""
+    L = load_library()
+    h = np.ascontiguousarray(hash20, dtype=np.uint32); out = np.empty(len(h), dtype=np.uint32)
+    rc = L.sage_robin_iteration_order(h.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(len(h)), out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if rc != 0:
+        raise _err(L, "sage_robin_iteration_order", rc)
+    return out
+
+
 def nccl_unique_id() -> bytes:
     L = load_library()
     buf = (C.c_uint8 * 128)()

@@ -325,6 +325,13 @@ int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms) {
 size_t sage_debug_timeline(sage_map *m, unsigned long long *out, size_t cap) { return m->impl->debug_timeline(out, cap); }
 int64_t sage_launch_count(void) { return g_launches.load(); }
 
+int sage_robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out) {
+    return (int)guarded([&] {
+        if (n && (!hash20 || !order_out)) throw ArgError("null argument");
+        robin_iteration_order(hash20, n, order_out);
+        return 0;
+    });
+}
 int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end) {
     if (world < 1 || rank < 0 || rank >= world || !begin || !end) {
         g_err = "bad shard arguments";

@@ -116,3 +116,30 @@ def test_config_pod_layout_matches_the_header(cfg):
         assert int(out[f]) == getattr(ConfigPOD, f).offset, f
     pod = cfg.to_pod()
     assert pod.n_groups == len(cfg.voxel_labels) == 6 and pod.voxel_size_map == 0.8 and pod.sem_th == 0.4
+
+
+@pytest.mark.parametrize("n,spread,seed", [(0, 3, 0), (1, 3, 1), (2, 3, 2), (300, 3, 3), (2049, 20, 4), (9000, 60, 5), (40000, 200, 6)])
+def test_product_robin_replay_matches_the_oracle_table(lib, orc, n, spread, seed):
+    """The product's own host-side replay of the tsl::robin_map order (csrc/frontend.cu, used by VoxelDownsample) against the
+    oracle's RobinTable — two independent implementations of the same published rules (and the oracle one is itself pinned
+    against a pure-Python emulator in test_oracle_robin.py)."""
+    import sage_icp_b200 as sg
+    rng = np.random.default_rng(seed)
+    keys = np.unique(rng.integers(-spread, spread + 1, size=(4 * max(n, 1), 3)), axis=0)
+    rng.shuffle(keys)
+    keys = keys[:n].astype(np.int32)
+    h = np.array([orc.voxel_hash(*[int(v) for v in k]) for k in keys], dtype=np.uint32)
+    got = sg.robin_iteration_order(h)
+    want, _ = orc.robin_order(keys) if len(keys) else (np.zeros(0, np.int64), 0)
+    assert np.array_equal(got.astype(np.int64), want)
+
+
+def test_product_robin_replay_with_saturated_hash(lib, orc):
+    """Many keys on few hash values: long probe sequences, the regime of SURVEY.md A.9 in miniature."""
+    import sage_icp_b200 as sg
+    keys = np.array([[(i % 7) + ((i // 7) << 20), 0, 0] for i in range(3000)], dtype=np.int64).astype(np.int32)  # 7 distinct 20-bit hashes
+    h = np.array([orc.voxel_hash(int(k[0]), 0, 0) for k in keys], dtype=np.uint32)
+    assert len(np.unique(h)) == 7
+    got = sg.robin_iteration_order(h)
+    want, _ = orc.robin_order(keys)
+    assert np.array_equal(got.astype(np.int64), want)

@@ -64,6 +64,17 @@ def make_queries(step: int, n_beams: int, n_az: int, half_len: float):
     return scan, guess
 
 
+def shard_of(scan: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Rank `rank`'s share of a scan.  Any partition gives the same sums; chunks of 32 consecutive points dealt round-robin
+    keep every rank's share a cross-section of the scan (a contiguous split, sage_shard_range, hands one rank all the far,
+    expensive beams)."""
+    if world == 1:
+        return np.ascontiguousarray(scan)
+    n_chunks = (len(scan) + 31) // 32
+    owner = np.repeat(np.arange(n_chunks) % world, 32)[: len(scan)]
+    return np.ascontiguousarray(scan[owner == rank])
+
+
 def algorithmic_bytes(n_q: int, occupied: int, candidates: int) -> float:
     """N_q*(16 + 27*8) + sum(4 + 16*n_v) + 27*8 per Gauss-Newton iteration."""
     return n_q * (16 + 27 * 8) + 4.0 * occupied + 16.0 * candidates + 27 * 8
@@ -181,7 +192,8 @@ def workload_config(args, map_points, map_voxels):
             "scan_rays": args.beams * args.az, "map_points": int(map_points), "map_voxels": int(map_voxels), "gn_iterations": ITERS,
             "max_correspondence_distance": MAX_DIST, "kernel": KERNEL, "sem_th": SEM_TH,
             "l2": "L2 flushed (256 MiB write) between timed steps; each step timed with its own CUDA-event pair",
-            "parallelism": f"query-shard x{args.gpus} + replicated map" if args.gpus > 1 else "single GPU"}
+            "parallelism": (f"query-shard x{args.gpus} + replicated map, all-reduce of the 17 normal-equation sums "
+                            + ("fused into the search kernel over NVLink peer memory" if args.comm == "peer" else "by NCCL")) if args.gpus > 1 else "single GPU"}
 
 
 def main():
@@ -202,6 +214,8 @@ def main():
     ap.add_argument("--az", type=int, default=1875)
     ap.add_argument("--cpu-fraction", type=float, default=0.1, help="fraction of each scan the CPU arm times")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: all-reduce of the normal equations fused into the search kernel over NVLink peer memory, or NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -233,14 +247,20 @@ def main():
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(sg.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
-        gmap.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        if args.comm == "nccl":
+            gmap.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        else:
+            mine = torch.frombuffer(bytearray(gmap.comm_peer_handle()), dtype=torch.uint8).cuda()
+            allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            gmap.comm_peer_attach(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+            dist.barrier()
 
     total = args.warmup + args.steps
     scans, guesses, shards_dev, shards_pin = [], [], [], []
     for s in range(total):
         scan, guess = make_queries(s, args.beams, args.az, half)
-        b, e = sg.shard_range(len(scan), rank, world)
-        shard = np.ascontiguousarray(scan[b:e])
+        shard = shard_of(scan, rank, world)
         scans.append(scan); guesses.append(guess)
         shards_dev.append(torch.from_numpy(shard).cuda())
         shards_pin.append(torch.from_numpy(shard).pin_memory())

@@ -202,6 +202,14 @@ int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end);
  * frame as this rank's shard and all-reduces the normal-equation sums (17 doubles) every iteration. */
 int sage_nccl_unique_id(uint8_t id_out[128]);
 int sage_map_comm_init(sage_map *m, int rank, int world, const uint8_t id[128]);
+/* Fused alternative for the GPUs of ONE NVLink/NVSwitch box (one process per GPU): the all-reduce happens inside the search
+ * kernel — every rank's last block stores its 17 sums straight into every peer's exchange buffer (CUDA IPC peer mappings)
+ * and adds the slots in rank order, so an iteration stays a single launch.  Every rank calls sage_map_comm_peer_handle,
+ * the 64-byte handles are gathered by any means (rank order), then every rank calls sage_map_comm_peer_attach with all of
+ * them.  Takes precedence over the NCCL path when both are set up.  A rank that does not arrive within 2 s ends the
+ * registration with SAGE_ECUDA. */
+int sage_map_comm_peer_handle(sage_map *m, uint8_t handle_out[64]);
+int sage_map_comm_peer_attach(sage_map *m, int rank, int world, const uint8_t *handles /* world x 64 bytes */);
 int sage_map_comm_destroy(sage_map *m);
 
 #ifdef __cplusplus

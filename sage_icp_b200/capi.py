@@ -248,6 +248,16 @@ class SageMap:
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         self._chk(self.L.sage_map_comm_init(self.h, rank, world, buf), "sage_map_comm_init")
 
+    def comm_peer_handle(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._chk(self.L.sage_map_comm_peer_handle(self.h, buf), "sage_map_comm_peer_handle")
+        return bytes(buf)
+
+    def comm_peer_attach(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == 64 * world
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._chk(self.L.sage_map_comm_peer_attach(self.h, rank, world, buf), "sage_map_comm_peer_attach")
+
     def comm_destroy(self): self._chk(self.L.sage_map_comm_destroy(self.h), "sage_map_comm_destroy")
 
 

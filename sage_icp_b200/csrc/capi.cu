@@ -354,9 +354,22 @@ int sage_map_comm_init(sage_map *m, int rank, int world, const uint8_t id[128]) 
         return 0;
     });
 }
+int sage_map_comm_peer_handle(sage_map *m, uint8_t handle_out[64]) {
+    return (int)guarded([&] {
+        m->impl->peer_handle(handle_out);
+        return 0;
+    });
+}
+int sage_map_comm_peer_attach(sage_map *m, int rank, int world, const uint8_t *handles) {
+    return (int)guarded([&] {
+        m->impl->peer_attach(rank, world, handles);
+        return 0;
+    });
+}
 int sage_map_comm_destroy(sage_map *m) {
     return (int)guarded([&] {
         m->impl->comm_destroy();
+        m->impl->peer_detach();
         return 0;
     });
 }

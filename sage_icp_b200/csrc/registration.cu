@@ -34,6 +34,8 @@ constexpr int kNnThreads = SAGE_NN_THREADS;
 static_assert(kNnThreads % 32 == 0 && (kNnThreads / 32) * 3 >= 17, "the last-block reduction gives each warp up to three of the 17 sums");
 constexpr int kSums = 17;
 constexpr int kDbg = 12;  // debug timeline stamps per block
+constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
+constexpr int kXchgSlot = 24;  // doubles per (parity, source rank) slot: 17 sums + tag, padded to 192 bytes
 
 
 struct IterParams {
@@ -58,6 +60,11 @@ struct IterParams {
     int solve;
     int respect_done;
     int all_warp;      // 1: warp-per-query for every query (small scans)
+    // fused all-reduce over NVLink peer memory (multi-GPU): xchg_peer[k] = rank k's exchange buffer mapped here (CUDA IPC),
+    // laid out [parity][source rank][kXchgSlot]; xchg_tag = this launch's sequence number (same on every rank)
+    int xchg_world, xchg_rank;
+    double *xchg_peer[kMaxPeers];
+    unsigned long long xchg_tag;
     int light_probes;  // neighbour probes a query may spend in the thread-per-query phase before it is deferred
     unsigned long long *dbg;  // optional per-block timeline (tools/perf_probe.py): 4 globaltimer stamps per block + 4 global
 };
@@ -153,6 +160,7 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->ticket = 0;
     st->stat_occupied = st->stat_candidates = 0;
     st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = 0;
+    st->comm_error = 0;
 }
 
 __global__ void icp_solve_kernel(IcpState *st) {  // <<<1, 64>>>, after the NCCL all-reduce of the sums
@@ -700,11 +708,50 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
         }
     }
     __syncthreads();
+    if (p.xchg_world > 1) {
+        // All-reduce of the 17 sums fused into this kernel: every rank's last block stores its sums, then the launch's tag,
+        // into its slot of EVERY peer's exchange buffer (plain stores over NVLink/NVSwitch peer mappings), waits until the
+        // slots of all ranks in its own buffer carry the tag, and adds them in rank order — the same values in the same
+        // order on every rank, so all replicas take the bit-identical Gauss-Newton step.  Slots alternate by tag parity: a
+        // rank can be at most one exchange ahead of a peer.  A peer that never shows up (2 s) ends the registration.
+        const int t = threadIdx.x;
+        const size_t slot = ((size_t)(p.xchg_tag & 1ull) * kMaxPeers) * kXchgSlot;
+        if (t < p.xchg_world) {
+            double *dst = p.xchg_peer[t] + slot + (size_t)p.xchg_rank * kXchgSlot;
+#pragma unroll
+            for (int k = 0; k < kSums; ++k) dst[k] = st->sums[k];
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(dst + kSums) = p.xchg_tag;
+        }
+        __syncthreads();
+        if (t < p.xchg_world) {
+            const volatile unsigned long long *flag =
+                reinterpret_cast<const volatile unsigned long long *>(p.xchg_peer[p.xchg_rank] + slot + (size_t)t * kXchgSlot + kSums);
+            const unsigned long long t0 = gtime();
+            while (*flag != p.xchg_tag) {
+                if (gtime() - t0 > 2000000000ull) {
+                    st->comm_error = 1;
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (t < kSums) {
+            const volatile double *mine = p.xchg_peer[p.xchg_rank] + slot;
+            double v = 0;
+            for (int r = 0; r < p.xchg_world; ++r) v += mine[(size_t)r * kXchgSlot + t];
+            st->sums[t] = v;
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         st->ticket = 0;
         if (p.dbg) p.dbg[kDbg * gridDim.x + 1] = gtime();
+        if (p.xchg_world > 1 && st->comm_error) st->done = 1;
     }
-    if (p.solve) icp_step_block(st, &s_est, &s_norm);
+    __syncthreads();
+    if (p.solve && !(p.xchg_world > 1 && st->comm_error)) icp_step_block(st, &s_est, &s_norm);
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
 }
 
@@ -794,7 +841,14 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     p.dbg = (mode == 0 && dbg_on_) ? dbg_.p : nullptr;
     p.light_probes = light_probes_, p.all_warp = all_warp ? 1 : 0;
     p.apply_est = (mode == 0), p.respect_done = (mode == 0);
-    p.solve = (mode == 0 && comm_ == nullptr);
+    p.solve = (mode == 0 && comm_ == nullptr);  // NCCL path: all-reduce and solve are separate launches
+    p.xchg_world = 1, p.xchg_rank = 0, p.xchg_tag = 0;
+    for (int k = 0; k < kMaxPeers; ++k) p.xchg_peer[k] = nullptr;
+    if (mode == 0 && peer_world_ > 1) {  // fused peer-memory all-reduce: one launch per iteration does everything
+        p.solve = 1;
+        p.xchg_world = peer_world_, p.xchg_rank = peer_rank_, p.xchg_tag = ++xchg_tag_;
+        for (int k = 0; k < peer_world_; ++k) p.xchg_peer[k] = peer_buf_[k];
+    }
 
     const bool prof = profile_ && mode == 0;
     if (prof) {
@@ -814,7 +868,7 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].second, stream_));
         ++prof_used_;
     }
-    if (mode == 0 && comm_ != nullptr) {
+    if (mode == 0 && comm_ != nullptr && peer_world_ <= 1) {
         nccl_allreduce_sum_f64(comm_, icp_.p->sums, kSums, stream_);
         SAGE_LAUNCH(icp_solve_kernel, 1, 64, 0, stream_, icp_.p);
     }
@@ -848,6 +902,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
         SAGE_CUDA(cudaStreamSynchronize(stream_));
         if (icp_pin_.p->done) break;
     }
+    if (icp_pin_.p->comm_error) throw CudaError("peer exchange timed out: a rank of the sharded registration did not arrive (nccl/peer)");
     pose_out = icp_pin_.p->result;
     last_iters_ = icp_pin_.p->iter;
     return icp_pin_.p->iter;

@@ -249,6 +249,8 @@ VoxelMapGPU::~VoxelMapGPU() {
     cudaSetDevice(device_);
     if (stream_) cudaStreamSynchronize(stream_);
     comm_destroy();
+    peer_detach();
+    if (xchg_local_) cudaFree(xchg_local_);
     for (auto &e : prof_events_) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -459,6 +461,49 @@ void VoxelMapGPU::comm_init(int rank, int world, const uint8_t id[128]) {
     set_device();
     comm_destroy();
     comm_ = nccl_comm_create(rank, world, id);
+}
+
+// ---- fused all-reduce over NVLink peer memory ------------------------------------------------------------------
+constexpr size_t kXchgDoubles = 2 * 8 * 24;  // [parity][source rank][slot], see registration.cu
+
+void VoxelMapGPU::peer_handle(uint8_t out[64]) {
+    set_device();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!xchg_local_) SAGE_CUDA(cudaMalloc(&xchg_local_, kXchgDoubles * sizeof(double)));
+    // tags restart at 1 after every attach: clear stale ones now, before any peer can hold this buffer's handle
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    SAGE_CUDA(cudaMemset(xchg_local_, 0, kXchgDoubles * sizeof(double)));
+    SAGE_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    SAGE_CUDA(cudaIpcGetMemHandle(&h, xchg_local_));
+    std::memcpy(out, &h, 64);
+}
+
+void VoxelMapGPU::peer_attach(int rank, int world, const uint8_t *handles) {
+    set_device();
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) throw ArgError("peer_attach: 1..8 ranks of one node");
+    if (!xchg_local_) throw ArgError("peer_attach: call sage_map_comm_peer_handle first");
+    peer_detach();
+    for (int k = 0; k < world; ++k) {
+        if (k == rank) {
+            peer_buf_[k] = xchg_local_;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + 64 * (size_t)k, 64);
+        void *ptr = nullptr;
+        SAGE_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        peer_buf_[k] = (double *)ptr;
+    }
+    peer_rank_ = rank, peer_world_ = world, xchg_tag_ = 0;
+}
+
+void VoxelMapGPU::peer_detach() {
+    for (int k = 0; k < 8; ++k) {
+        if (peer_buf_[k] && peer_buf_[k] != xchg_local_) cudaIpcCloseMemHandle(peer_buf_[k]);
+        peer_buf_[k] = nullptr;
+    }
+    peer_world_ = 0;
 }
 
 void VoxelMapGPU::comm_destroy() {

@@ -73,6 +73,10 @@ public:
 
     void comm_init(int rank, int world, const uint8_t id[128]);
     void comm_destroy();
+    // fused all-reduce over peer memory: export this rank's exchange buffer, then attach every rank's
+    void peer_handle(uint8_t out[64]);
+    void peer_attach(int rank, int world, const uint8_t *handles);
+    void peer_detach();
 
     // statistics mirror (refreshed by sync_stats)
     void sync_stats();
@@ -134,6 +138,10 @@ private:
     size_t prof_used_ = 0;
 
     NcclComm *comm_ = nullptr;
+    double *peer_buf_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [rank] -> mapped exchange buffer
+    double *xchg_local_ = nullptr;
+    int peer_rank_ = 0, peer_world_ = 0;
+    unsigned long long xchg_tag_ = 0;
 };
 
 }  // namespace sage

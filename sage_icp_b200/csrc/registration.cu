@@ -810,7 +810,7 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         nn_grid_ = sm_count_ * (per_sm > 0 ? per_sm : 1);
         partials_.ensure((size_t)kSums * nn_grid_);
         if (const char *e = getenv("SAGE_LIGHT_PROBES")) light_probes_ = atoi(e);  // tuning knobs
-        all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 2;
+        all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 3 / 4;
         if (const char *e = getenv("SAGE_ALL_WARP_MAX")) all_warp_max_ = (size_t)atol(e);
     }
     // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
@@ -839,7 +839,11 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     }
     p.st = icp_.p, p.partials = partials_.p, p.tgt_out = tgt_out, p.matched_out = matched_out;
     p.dbg = (mode == 0 && dbg_on_) ? dbg_.p : nullptr;
-    p.light_probes = light_probes_, p.all_warp = all_warp ? 1 : 0;
+    // Neighbour probes a query may spend in the thread-per-query phase before it is deferred to the warp phase: the fewer
+    // queries there are, the more idle warps the deferred phase finds, so the earlier it pays to hand a query over
+    // (measured on B200, profiles/r01g_nn_search_kernel_ncu.md: best of 1/2/3/5/8 at each size).
+    const int auto_probes = n <= 20000 ? 1 : (n <= 90000 ? 3 : 8);
+    p.light_probes = light_probes_ >= 0 ? light_probes_ : auto_probes, p.all_warp = all_warp ? 1 : 0;
     p.apply_est = (mode == 0), p.respect_done = (mode == 0);
     p.solve = (mode == 0 && comm_ == nullptr);  // NCCL path: all-reduce and solve are separate launches
     p.xchg_world = 1, p.xchg_rank = 0, p.xchg_tag = 0;

@@ -128,7 +128,7 @@ private:
     int nn_grid_ = 0;
     size_t all_warp_max_ = 0;  // scans up to this many queries use the warp-per-query mode
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
-    int light_probes_ = 8;  // neighbour probes per query in the thread-per-query phase before the query is deferred
+    int light_probes_ = -1;  // < 0: chosen from the number of queries (launch_iteration); SAGE_LIGHT_PROBES overrides
     bool dbg_on_ = false;
     DevBuf<unsigned long long> dbg_;
 

@@ -108,20 +108,41 @@ __device__ __forceinline__ double shfl_d(unsigned mask, double v, int lane) { re
 // |log(est)| < threshold (core/Registration.cpp:92-93,133-137).  Called by EVERY thread of a block of >= 64 threads (it
 // synchronises): thread 0 solves and exponentiates, then thread 0 (pose products) and thread 32 (log norm) run side by side.
 __device__ __noinline__ void icp_solve_xi(const double *S, double xi[6]) {
-    // JTJ = sum w [[I, -s^],[s^, |s|^2 I - s s^T]],  JTr = sum w [r; s x r]   
+    // Normal equations with s = sum w s, r_t = sum w r, r_r = sum w (s x r):
+    //   JTJ = [[ w I, -[s]x ], [ [s]x, C ]],  C = sum w (|s|^2 I - s s^T),   JTJ (u, o) = -(r_t, r_r).
+    // The translation block is w I, so the 6x6 system collapses exactly onto its 3x3 Schur complement
+    //   (C - (|s|^2 I - s s^T) / w) o = -r_r + (s x r_t) / w,      u = (-r_t - o x s) / w,
+    // i.e. the second moments about the weighted centroid: better conditioned than the raw 6x6 (whose entries grow like
+    // |s|^2) and ~5 us cheaper than a pivoted 6x6 LDLT in one thread.  Same solution as the reference's
+    // JTJ.ldlt().solve(-JTr) (core/Registration.cpp:92) up to rounding (~1e-12 relative; tolerance is 1e-4 m / 1e-5 rad).
     const double w = S[0], x = S[1], y = S[2], z = S[3], xx = S[4], yy = S[5], zz = S[6], xy = S[7], xz = S[8], yz = S[9];
-    double A[6][6] = {{w, 0, 0, 0, z, -y},       {0, w, 0, -z, 0, x},        {0, 0, w, y, -x, 0},
-                      {0, -z, y, yy + zz, -xy, -xz}, {z, 0, -x, -xy, xx + zz, -yz}, {-y, x, 0, -xz, -yz, xx + yy}};
-    double b[6];
+    const double btx = -S[10], bty = -S[11], btz = -S[12], brx = -S[13], bry = -S[14], brz = -S[15];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) b[i] = -S[10 + i];
-    solve6_ldlt_static(A, b, xi);
+    for (int i = 0; i < 6; ++i) xi[i] = 0.0;
+    if (!(w > 0.0)) return;  // no correspondence: zero step, as the reference's LDLT of a zero matrix
+    const double iw = 1.0 / w;
+    const double m00 = (yy + zz) - (y * y + z * z) * iw, m11 = (xx + zz) - (x * x + z * z) * iw, m22 = (xx + yy) - (x * x + y * y) * iw;
+    const double m01 = -xy + x * y * iw, m02 = -xz + x * z * iw, m12 = -yz + y * z * iw;
+    // rhs = b_r - (s x b_t) / w
+    const double qx = brx - (y * btz - z * bty) * iw, qy = bry - (z * btx - x * btz) * iw, qz = brz - (x * bty - y * btx) * iw;
+    // symmetric 3x3 solve by cofactors
+    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+    const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+    const double det = m00 * c00 + m01 * c01 + m02 * c02;
+    if (det == 0.0 || !(det == det)) return;
+    const double id = 1.0 / det;
+    const double ox = (c00 * qx + c01 * qy + c02 * qz) * id, oy = (c01 * qx + c11 * qy + c12 * qz) * id, oz = (c02 * qx + c12 * qy + c22 * qz) * id;
+    // u = (b_t - o x s) / w
+    xi[0] = (btx - (oy * z - oz * y)) * iw, xi[1] = (bty - (oz * x - ox * z)) * iw, xi[2] = (btz - (ox * y - oy * x)) * iw;
+    xi[3] = ox, xi[4] = oy, xi[5] = oz;
 }
-__device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, double *s_norm) {
+__device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
     if (threadIdx.x == 0) {
         double xi[6];
         icp_solve_xi(st->sums, xi);
+        if (dbg) dbg[5] = gtime();
         *s_pose = pose_exp(xi);
+        if (dbg) dbg[6] = gtime();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -751,7 +772,7 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
         if (p.xchg_world > 1 && st->comm_error) st->done = 1;
     }
     __syncthreads();
-    if (p.solve && !(p.xchg_world > 1 && st->comm_error)) icp_step_block(st, &s_est, &s_norm);
+    if (p.solve && !(p.xchg_world > 1 && st->comm_error)) icp_step_block(st, &s_est, &s_norm, p.dbg ? p.dbg + kDbg * gridDim.x : nullptr);
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
 }
 
@@ -989,7 +1010,7 @@ size_t VoxelMapGPU::debug_timeline(unsigned long long *out, size_t cap) {
     dbg_on_ = true;
     dbg_.ensure((size_t)kDbg * 4096 + 8);
     SAGE_CUDA(cudaStreamSynchronize(stream_));
-    const size_t n = (size_t)kDbg * (nn_grid_ > 0 ? nn_grid_ : 1) + 4;
+    const size_t n = (size_t)kDbg * (nn_grid_ > 0 ? nn_grid_ : 1) + 8;
     if (out && cap >= n) SAGE_CUDA(cudaMemcpy(out, dbg_.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return n;
 }

@@ -34,12 +34,12 @@ pose, it = m.register_frame(scan, guess, 3.0, 1/3, 0.4, max_iters=3, est_th=0.0)
 buf = np.zeros(n, np.uint64)
 L.sage_debug_timeline(m.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_size_t(n))
 K = 12
-g = int(buf[n - 1]); b = buf[:K * g].reshape(g, K).astype(np.int64); tail = buf[K * g:K * g + 3].astype(np.int64)
+g = (n - 8) // K; b = buf[:K * g].reshape(g, K).astype(np.int64); tail = buf[K * g:K * g + 8].astype(np.int64)
 t0 = b[:, 0].min()
 pc = lambda a, q: np.percentile(a - t0, q)
 print(f"timeline ns, grid {g}: start max {b[:,0].max()-t0} | warp0 light done med {pc(b[:,1],50):.0f} | block light done med {pc(b[:,2],50):.0f} p90 {pc(b[:,2],90):.0f} "
       f"max {pc(b[:,2],100):.0f} | block all done med {pc(b[:,3],50):.0f} p90 {pc(b[:,3],90):.0f} max {pc(b[:,3],100):.0f} | "
-      f"last block: enter {tail[0]-t0} reduced {tail[1]-t0} solved {tail[2]-t0}")
+      f"last block: enter {tail[0]-t0} reduced {tail[1]-t0} | 6x6 solved {tail[5]-t0} exp done {tail[6]-t0} step done {tail[2]-t0}")
 names = ["start", "loaded+transformed", "home probed", "home scanned", "neighbours done", "exact done", "accumulated"]
 cols = [0, 4, 5, 6, 7, 8, 9]
 prev = b[:, 0]

@@ -3,7 +3,7 @@
 //   SE3d::exp / log      core/Registration.cpp:93,137
 //   SE3d * SE3d, inverse pipeline/sageICP.cpp:76,90,114,119
 //   SE3d * Vector3d      core/Registration.cpp:106 (Eigen quaternion _transformVector form)
-//   6x6 ldlt().solve     core/Registration.cpp:92
+//   (the 6x6 ldlt().solve of core/Registration.cpp:92 is done through its 3x3 Schur complement in registration.cu)
 #pragma once
 #include <cmath>
 
@@ -147,112 +147,6 @@ SAGE_HD void pose_log(const Pose &T, double xi[6]) {
 SAGE_HD double pose_rotation_angle(const Pose &T) {
     const double n = sqrt((T.qx * T.qx + T.qy * T.qy) + T.qz * T.qz);
     return (n != 0.0) ? 2.0 * atan2(n, fabs(T.qw)) : 0.0;
-}
-
-// Symmetric 6x6 solve A x = b by LDL^T with diagonal pivoting (largest |A_ii|), as Eigen's LDLT does.
-SAGE_HD void solve6_ldlt(double A[6][6], const double bin[6], double x[6]) {
-    int perm[6];
-    for (int i = 0; i < 6; ++i) perm[i] = i;
-    for (int k = 0; k < 6; ++k) {
-        int p = k;
-        double best = fabs(A[k][k]);
-        for (int i = k + 1; i < 6; ++i)
-            if (fabs(A[i][i]) > best) best = fabs(A[i][i]), p = i;
-        if (p != k) {
-            for (int j = 0; j < 6; ++j) {
-                const double t = A[k][j];
-                A[k][j] = A[p][j], A[p][j] = t;
-            }
-            for (int i = 0; i < 6; ++i) {
-                const double t = A[i][k];
-                A[i][k] = A[i][p], A[i][p] = t;
-            }
-            const int t = perm[k];
-            perm[k] = perm[p], perm[p] = t;
-        }
-        const double d = A[k][k];
-        if (d == 0.0) continue;
-        for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
-        for (int i = k + 1; i < 6; ++i)
-            for (int j = k + 1; j <= i; ++j) {
-                A[i][j] -= A[i][k] * d * A[j][k];
-                A[j][i] = A[i][j];
-            }
-    }
-    double y[6];
-    for (int i = 0; i < 6; ++i) y[i] = bin[perm[i]];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
-    for (int i = 0; i < 6; ++i) y[i] = (A[i][i] != 0.0) ? y[i] / A[i][i] : 0.0;
-    for (int i = 5; i >= 0; --i)
-        for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-    for (int i = 0; i < 6; ++i) x[perm[i]] = y[i];
-}
-
-// Same algorithm and operation order as solve6_ldlt, written so that every array index is a compile-time constant after
-// unrolling (the pivot interchange is a chain of predicated static swaps): the matrix lives in registers instead of
-// local memory.  Bit-identical results.
-SAGE_HD void solve6_ldlt_static(double A[6][6], const double bin[6], double x[6]) {
-    int perm[6] = {0, 1, 2, 3, 4, 5};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        int p = k;
-        double best = fabs(A[k][k]);
-#pragma unroll
-        for (int i = k + 1; i < 6; ++i)
-            if (fabs(A[i][i]) > best) best = fabs(A[i][i]), p = i;
-#pragma unroll
-        for (int c = k + 1; c < 6; ++c)
-            if (p == c) {
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    const double t = A[k][j];
-                    A[k][j] = A[c][j], A[c][j] = t;
-                }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const double t = A[i][k];
-                    A[i][k] = A[i][c], A[i][c] = t;
-                }
-                const int t = perm[k];
-                perm[k] = perm[c], perm[c] = t;
-            }
-        const double d = A[k][k];
-        if (d != 0.0) {
-#pragma unroll
-            for (int i = k + 1; i < 6; ++i) A[i][k] /= d;
-#pragma unroll
-            for (int i = k + 1; i < 6; ++i)
-#pragma unroll
-                for (int j = k + 1; j <= i; ++j) {
-                    A[i][j] -= A[i][k] * d * A[j][k];
-                    A[j][i] = A[i][j];
-                }
-        }
-    }
-    double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        y[i] = 0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-            if (perm[i] == j) y[i] = bin[j];
-    }
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < i; ++j) y[i] -= A[i][j] * y[j];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] = (A[i][i] != 0.0) ? y[i] / A[i][i] : 0.0;
-#pragma unroll
-    for (int i = 5; i >= 0; --i)
-#pragma unroll
-        for (int j = i + 1; j < 6; ++j) y[i] -= A[j][i] * y[j];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-            if (perm[i] == j) x[j] = y[i];
 }
 
 }  // namespace sage

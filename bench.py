@@ -247,14 +247,32 @@ def main():
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(sg.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
-        if args.comm == "nccl":
-            gmap.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
-        else:
-            mine = torch.frombuffer(bytearray(gmap.comm_peer_handle()), dtype=torch.uint8).cuda()
+        comm_used = args.comm
+        if args.comm == "peer":
+            # collective decision: if CUDA IPC / peer access fails on ANY rank, every rank falls back to NCCL
+            ok = 1
+            try:
+                mine = torch.frombuffer(bytearray(gmap.comm_peer_handle()), dtype=torch.uint8).cuda()
+            except sg.SageError as e:
+                print(f"[rank {rank}] peer handle failed: {e}", file=sys.stderr)
+                mine, ok = torch.zeros(64, dtype=torch.uint8, device="cuda"), 0
             allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(allh, mine)
-            gmap.comm_peer_attach(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
-            dist.barrier()
+            if ok:
+                try:
+                    gmap.comm_peer_attach(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+                except sg.SageError as e:
+                    print(f"[rank {rank}] peer attach failed: {e}", file=sys.stderr)
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                gmap.comm_destroy()
+                comm_used = "nccl"
+        if comm_used == "nccl":
+            gmap.comm_init(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        args.comm = comm_used
+        dist.barrier()
 
     total = args.warmup + args.steps
     scans, guesses, shards_dev, shards_pin = [], [], [], []

@@ -833,11 +833,12 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         if (const char *e = getenv("SAGE_LIGHT_PROBES")) light_probes_ = atoi(e);  // tuning knobs
         all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 3 / 4;
         if (const char *e = getenv("SAGE_ALL_WARP_MAX")) all_warp_max_ = (size_t)atol(e);
+        if (getenv("SAGE_NO_ALL_WARP")) all_warp_max_ = 0;
     }
     // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
     // there is a chunk for every block, fewer blocks for small scans
     // small scans: one warp per query (all_warp) as long as that is at most two queries per resident warp
-    const bool all_warp = n <= all_warp_max_ && !getenv("SAGE_NO_ALL_WARP");
+    const bool all_warp = n <= all_warp_max_;
     uint32_t grid = all_warp ? (uint32_t)((n + kNnThreads / 32 - 1) / (kNnThreads / 32)) : (uint32_t)((n + 31) / 32);
     grid = grid < 1 ? 1 : (grid > (uint32_t)nn_grid_ ? (uint32_t)nn_grid_ : grid);
 

@@ -150,27 +150,59 @@ __device__ __forceinline__ void add_point_rule(const MapView &m, double4 *vox, f
         }
 }
 
-// phase 3: the thread whose point was pushed first (next == nil) replays that voxel's arrivals in input order
+// Bottom-up merge sort of a voxel's arrival list by point index (the list is built by atomicExch, i.e. in arbitrary order; the
+// reference inserts in input order).  O(k log k) pointer steps, no extra memory: a degenerate batch that puts 10^5 points into
+// one voxel costs a second, not the hours a quadratic selection would.
+__device__ uint32_t sort_arrivals(uint32_t head, uint32_t *next) {
+    for (uint32_t insize = 1;; insize *= 2) {
+        uint32_t p = head, tail = kNil, nmerges = 0;
+        head = kNil;
+        while (p != kNil) {
+            ++nmerges;
+            uint32_t q = p, psize = 0, qsize = insize;
+            for (uint32_t i = 0; i < insize; ++i) {
+                ++psize;
+                q = next[q];
+                if (q == kNil) break;
+            }
+            while (psize > 0 || (qsize > 0 && q != kNil)) {
+                uint32_t e;
+                if (psize == 0) {
+                    e = q, q = next[q], --qsize;
+                } else if (qsize == 0 || q == kNil || p <= q) {
+                    e = p, p = next[p], --psize;
+                } else {
+                    e = q, q = next[q], --qsize;
+                }
+                if (tail != kNil)
+                    next[tail] = e;
+                else
+                    head = e;
+                tail = e;
+            }
+            p = q;
+        }
+        if (tail != kNil) next[tail] = kNil;
+        if (nmerges <= 1) return head;
+    }
+}
+
+// phase 3: the thread whose point is the head of its voxel's arrival list (the last one pushed) sorts the list into input order
+// and replays it.  Ownership is read from blk_head, which only the owner changes (to nil, when it is done): the `next` links are
+// rewritten by the sort and must not be used for that.
 __global__ void map_replay_kernel(MapView m, const double4 *pts, const uint32_t *slot, uint32_t *next, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || next[i] != kNil) return;
+    if (i >= n) return;
     const uint32_t s = slot[i];
+    if (s == kNil) return;  // key outside the packable range: dropped in phase 1
     const uint32_t b = m.tbl[s].block;
-    const uint32_t head = m.blk_head[b];
+    if (m.blk_head[b] != i) return;
     double4 *vox = m.blk_pts + (size_t)b * m.stride;
     float4 *hot = m.blk_hot + (size_t)b * m.stride;
     int kx, ky, kz;
     unpack_key(m.blk_key[b], kx, ky, kz);
     int cnt = m.blk_cnt[b];
-    long long last = -1;
-    while (true) {
-        uint32_t best = kNil;
-        for (uint32_t j = head; j != kNil; j = next[j])
-            if ((long long)j > last && j < best) best = j;
-        if (best == kNil) break;
-        add_point_rule(m, vox, hot, kx, ky, kz, cnt, pts[best]);
-        last = best;
-    }
+    for (uint32_t j = sort_arrivals(m.blk_head[b], next); j != kNil; j = next[j]) add_point_rule(m, vox, hot, kx, ky, kz, cnt, pts[j]);
     m.blk_cnt[b] = cnt;
     m.tbl[s].count = (uint32_t)cnt;
     m.blk_head[b] = kNil;

@@ -200,3 +200,21 @@ def test_nn_stats_match_oracle(orc):
     g.load(*o.dump())
     scan, _ = _query_cloud(17, 8000)
     assert g.nn_stats(scan) == o.nn_stats(scan)
+
+
+def test_degenerate_batch_into_one_voxel(orc):
+    """150 000 points of one batch in a single voxel (and 50 000 spread around): the per-voxel replay must stay in input order
+    and finish promptly (the arrival list is merge-sorted, not selected quadratically)."""
+    import time
+    g, o = _maps(orc)
+    rng = np.random.default_rng(8)
+    a = np.c_[rng.uniform(0.01, 0.79, (150_000, 3)), rng.choice([0, 40, 81], 150_000)]
+    b = np.c_[rng.uniform(-20, 20, (50_000, 3)), rng.choice([0, 40, 81], 50_000)]
+    pts = np.concatenate([a, b])
+    rng.shuffle(pts)
+    t = time.time()
+    g.add_points(pts)
+    assert g.num_voxels() > 1000
+    assert time.time() - t < 20.0
+    o.add_points(pts)
+    assert_maps_equal(g.dump(), o.dump())

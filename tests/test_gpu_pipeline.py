@@ -179,3 +179,23 @@ def test_register_frame_from_pointcloud2_buffer(orc, cfg, label_f32):
         assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD
     with pytest.raises(sg.SageError):
         a.register_frame_pointcloud2(buf, len(scan), 10, (0, 4, 8, 12), 2)  # offsets do not fit point_step
+
+
+def test_empty_and_tiny_frames_mid_sequence(orc, cfg):
+    """An empty scan, and one whose points are all cropped away, in the middle of a drive: no correspondences, the 6x6
+    system is zero, the step is the identity and the pose is the constant-velocity guess — on both sides."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    gp, op = sg.SagePipeline(cfg), orc.OraclePipeline(cfg, evict_faithful=False)
+    traj = syn.trajectory(6)
+    frames = [syn.make_scan(900 + i, tuple(traj[i]), n_beams=32, n_az=600) for i in range(6)]
+    frames[3] = np.zeros((0, 4))
+    frames[4] = np.array([[0.5, 0.2, 0.1, 40.0], [300.0, 1.0, 0.0, 50.0], [1.0, -1.0, 0.3, 81.0]])  # all outside (min_range, max_range)
+    for i, f in enumerate(frames):
+        pg, _, _ = gp.register_frame(f)
+        po, _, _ = op.register_frame(f)
+        dt, da = pose_delta(pg, po)
+        assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (i, dt, da)
+        assert gp.last_iterations() == op.last_iterations(), i
+        assert len(gp.last_source()) == len(op.last_source())
+    assert len(gp.poses()) == 6

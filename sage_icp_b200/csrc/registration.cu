@@ -31,7 +31,7 @@ namespace sage {
 #define SAGE_NN_THREADS 256
 #endif
 constexpr int kNnThreads = SAGE_NN_THREADS;
-static_assert(kNnThreads % 32 == 0 && (kNnThreads / 32) * 3 >= 17, "the last-block reduction gives each warp up to three of the 17 sums");
+static_assert(kNnThreads % 64 == 0 && kNnThreads >= 64, "whole warps, and icp_step_block needs two of them");
 constexpr int kSums = 17;
 constexpr int kDbg = 12;  // debug timeline stamps per block
 constexpr int kMaxPeers = 8;   // GPUs of one NVSwitch box
@@ -705,28 +705,20 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
     if (!s_last) return;
     __threadfence();
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x] = gtime();
-    // the last block adds the per-block partials: warp w owns sums w, w+8, w+16 (three independent chains); lane l adds
-    // blocks l, l+32, ... in order, then a fixed butterfly — the same tree for a given grid, so results are reproducible
-    {
-        const double *p0 = p.partials + (size_t)warp * gridDim.x, *p1 = p0 + (size_t)kWarps * gridDim.x, *p2 = p1 + (size_t)kWarps * gridDim.x;
-        const bool has2 = warp + 2 * kWarps < kSums;
-        double v0 = 0, v1 = 0, v2 = 0;
-#pragma unroll 4
-        for (uint32_t b = lane; b < gridDim.x; b += 32) {
-            v0 += __ldcg(p0 + b);
-            v1 += __ldcg(p1 + b);
-            if (has2) v2 += __ldcg(p2 + b);
+    // the last block adds the per-block partials: warp w owns sums w, w+W, w+2W, ...; lane l adds blocks l, l+32, ... in order
+    // (four loads in flight), then a fixed butterfly — the same tree for a given grid, so results are reproducible
+    for (int k = warp; k < kSums; k += kWarps) {
+        const double *pk = p.partials + (size_t)k * gridDim.x;
+        double v = 0;
+        uint32_t b = lane;
+        for (; b + 96 < gridDim.x; b += 128) {
+            const double a0 = __ldcg(pk + b), a1 = __ldcg(pk + b + 32), a2 = __ldcg(pk + b + 64), a3 = __ldcg(pk + b + 96);
+            v += a0, v += a1, v += a2, v += a3;
         }
+        for (; b < gridDim.x; b += 32) v += __ldcg(pk + b);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-        }
-        if (lane == 0) {
-            st->sums[warp] = v0, st->sums[warp + kWarps] = v1;
-            if (has2) st->sums[warp + 2 * kWarps] = v2;
-        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) st->sums[k] = v;
     }
     __syncthreads();
     if (p.xchg_world > 1) {

@@ -1,7 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout=400 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -12 gpurun_out/pytest_gpu.log
-timeout 200 python tools/perf_probe.py 2>&1 | grep -E "rep 2|timeline"
-timeout 500 python tools/stream_bench.py --frames 300 --cpu-frames 300 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('gpu_frames_per_s','gpu_ms_per_frame_median','mean_t_icp_ms','max_pose_delta_m','max_pose_delta_rad','mean_gn_iterations')})"
+timeout 300 python -m pytest tests/test_gpu_core.py tests/test_gpu_pipeline.py -m gpu -x -q --timeout=120 --timeout-method=thread 2>&1 | tail -2
+echo "== default (256 threads)"; timeout 200 python tools/perf_probe.py 2>&1 | grep -E "rep 2|timeline"
+for v in t128 t512; do echo "== variant $v"; SAGE_ICP_LIB=$PWD/sage_icp_b200/lib/variant_$v.so timeout 200 python tools/perf_probe.py 2>&1 | grep -E "rep 2|timeline"; done

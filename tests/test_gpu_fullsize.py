@@ -1,0 +1,70 @@
+"""BASELINE configs[1] at FULL size (120 000 queries, 5 M-point map): the oracle cannot register the full scan in seconds, so
+parity is checked on a 1/20 sample of the queries against the same full map, and the full run through properties the
+domain offers: permutation invariance of the pose, a zero step from the converged pose, and shard additivity of the sums."""
+import numpy as np
+import pytest
+
+from conftest import POSE_TOL_M, POSE_TOL_RAD, pose_delta
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def world(orc):
+    import sage_icp_b200 as sg
+    import bench
+    pts = bench.make_map_points(5_000_000)
+    g = sg.SageMap(bench.VOXEL_SIZE_MAP, 1e9, bench.BASIC, bench.CRITICAL, bench.BASIC_LABELS)
+    g.add_points(pts)
+    o = orc.OracleMap(bench.VOXEL_SIZE_MAP, 1e9, bench.BASIC, bench.CRITICAL, bench.BASIC_LABELS, evict_faithful=False)
+    o.add_points(pts)
+    scan, guess = bench.make_queries(0, 64, 1875, bench.street_half_length(5_000_000))
+    return g, o, scan, guess
+
+
+def test_full_map_same_voxels_and_points(world):
+    g, o, _, _ = world
+    assert g.num_voxels() == o.num_voxels() > 250_000
+    assert g.num_points() == o.num_points() > 4_900_000
+
+
+def test_sampled_queries_against_the_full_map(world, orc):
+    import bench
+    g, o, scan, guess = world
+    sub = np.ascontiguousarray(scan[::20])
+    pose_o, it_o = o.register_frame_core(sub, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH, threads=orc.max_threads(), max_iters=10, est_th=0.0)
+    pose_g, it_g = g.register_frame(sub, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH, max_iters=10, est_th=0.0)
+    dt, da = pose_delta(pose_g, pose_o)
+    assert it_g == it_o == 10 and dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (dt, da)
+    assert dt < 1e-9
+
+
+def test_full_scan_properties(world):
+    import bench
+    g, _, scan, guess = world
+    args = (bench.MAX_DIST, bench.KERNEL, bench.SEM_TH)
+    # permutation invariance: any order of the queries gives the same pose (sums differ only in rounding order)
+    pose10, it10 = g.register_frame(scan, guess, *args, max_iters=10, est_th=0.0)
+    perm = np.random.default_rng(0).permutation(len(scan))
+    pose_p, it_p = g.register_frame(np.ascontiguousarray(scan[perm]), guess, *args, max_iters=10, est_th=0.0)
+    dt, da = pose_delta(pose10, pose_p)
+    assert it_p == it10 == 10 and dt < 1e-9 and da < 1e-10
+    # run to convergence with the reference's limits (500 iterations, 1e-4): restarted from the converged pose the loop stops
+    # again within a few steps of the threshold's size (correspondences may still flip once or twice) and the pose barely moves
+    pose, it = g.register_frame(scan, guess, *args)
+    assert 3 <= it <= 500
+    if it < 500:
+        pose2, it2 = g.register_frame(scan, pose, *args)
+        dt, da = pose_delta(pose, pose2)
+        assert it2 <= 5 and dt < 5e-4 and da < 5e-5, (it, it2, dt, da)
+    # shard additivity: the normal equations of two halves add up to those of the whole scan (what the multi-GPU path relies on)
+    moved = scan.copy()
+    c, s = np.cos(2 * np.arctan2(guess[5], guess[6])), np.sin(2 * np.arctan2(guess[5], guess[6]))
+    moved[:, 0] = c * scan[:, 0] - s * scan[:, 1] + guess[0]
+    moved[:, 1] = s * scan[:, 0] + c * scan[:, 1] + guess[1]
+    moved[:, 2] = scan[:, 2] + guess[2]
+    A, b, n = g.normal_equations(moved, *args)
+    A0, b0, n0 = g.normal_equations(np.ascontiguousarray(moved[:60_000]), *args)
+    A1, b1, n1 = g.normal_equations(np.ascontiguousarray(moved[60_000:]), *args)
+    assert n == n0 + n1 > 100_000
+    assert np.allclose(A, A0 + A1, rtol=1e-12, atol=1e-6) and np.allclose(b, b0 + b1, rtol=1e-11, atol=1e-8)

@@ -105,3 +105,64 @@ def test_voxel_downsample_is_first_point_per_voxel_in_robin_order(orc, cfg):
             expect += t.order()
         assert np.array_equal(out, pts[expect])
         assert not np.isin(out[:, 3], [30, 252]).any()  # labels in no group are dropped (:69)
+
+
+class PyRobinMap(PyRobin):
+    """PyRobin plus tsl's erase (backward-shift deletion) and the reference's erase-while-iterating sweep."""
+
+    def erase_at(self, i):
+        mask = len(self.b) - 1
+        self.b[i] = None
+        prev, cur = i, (i + 1) & mask
+        while self.b[cur] is not None and self.b[cur][0] > 0:
+            self.b[prev] = self.b[cur]
+            self.b[prev][0] -= 1
+            self.b[cur] = None
+            prev, cur = cur, (cur + 1) & mask
+
+    def sweep(self, far):
+        """for (auto &[k, v] : map) if (far(v)) map.erase(k);  — the range-for's iterator is advanced AFTER the erase, from
+        the erased bucket, so whatever was shifted into it is not visited (core/VoxelHashMap.cpp:176-184)."""
+        i = 0
+        while i < len(self.b):
+            e = self.b[i]
+            if e is not None and far(e[2]):
+                self.erase_at(i)
+            i += 1
+
+
+@pytest.mark.parametrize("seed,max_distance", [(0, 12.0), (1, 6.0), (2, 25.0)])
+def test_faithful_eviction_matches_python_model(orc, seed, max_distance):
+    """RemovePointsFarFromLocation in the oracle's 'faithful' mode (erase while iterating a tsl::robin_map) against the
+    Python table: same survivors, same iteration order afterwards; and only far voxels may survive a sweep."""
+    rng = np.random.default_rng(seed)
+    vs = 1.0
+    pts = np.c_[rng.uniform(-30, 30, (6000, 3)) * [1, 1, 0.1], np.full(6000, 40.0)]
+    m = orc.OracleMap(vs, max_distance, 20, 20, [40], evict_faithful=True)
+    m.add_points(pts)
+    # python model: voxels in order of first appearance, value = first point of the voxel
+    t, seen = PyRobinMap(), {}
+    for p in pts:
+        k = tuple(int(v) for v in np.trunc(p[:3] / vs))
+        if k not in seen:
+            seen[k] = p[:3].copy()
+            t.insert(_hash(k), k)
+    keys0, _, _ = m.dump()
+    assert [tuple(int(v) for v in k) for k in keys0] == t.order()  # same table before the sweep
+    origin = np.array([4.0, -3.0, 0.0])
+    far = lambda k: ((seen[k] - origin) ** 2).sum() > max_distance ** 2
+    n_far0 = sum(far(k) for k in t.order())
+    for sweep in range(2):
+        m.remove_far(origin)
+        t.sweep(far)
+        keys, _, _ = m.dump()
+        got = [tuple(int(v) for v in k) for k in keys]
+        assert got == t.order(), sweep
+    survivors_far = [k for k in t.order() if far(k)]
+    # every erase can hide at most the one element shifted into its bucket: a sweep removes at least half of the far voxels
+    assert n_far0 > 100 and len(survivors_far) <= n_far0 // 4 + 1
+    clean = orc.OracleMap(vs, max_distance, 20, 20, [40], evict_faithful=False)
+    clean.add_points(pts)
+    clean.remove_far(origin)
+    ck, _, _ = clean.dump()
+    assert set(tuple(int(v) for v in k) for k in ck) == set(k for k in t.order() if not far(k)) | set()  # clean mode = exactly the near voxels

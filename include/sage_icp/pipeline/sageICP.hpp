@@ -10,7 +10,8 @@
 //
 // Differences a maintainer should know:
 //   * copies of a sageICP share one device pipeline (the reference deep-copies; the ROS node only move-assigns);
-//   * LocalMap() returns the same point set in device block order, not tsl::robin_map iteration order;
+//   * LocalMap() returns the same point set in device block order, and the map drops every far voxel; after
+//     SetReferenceMapSemantics(true) both follow the reference's tsl::robin_map (iteration order, erase-while-iterating sweep);
 //   * the default-constructed object owns no device state until it is assigned from sageICP(config)
 //     (the reference's default config has empty voxel_labels, which is undefined behaviour there: SURVEY.md A.11).
 #pragma once
@@ -179,6 +180,10 @@ public:
         if (handle_) Check(sage_reset(handle_.get()));
         return true;
     }
+    // Extension (not in the reference): true = reproduce the reference map's tsl::robin_map behaviour — the far voxels its
+    // erase-while-iterating sweep skips (core/VoxelHashMap.cpp:176-184) and LocalMap() in its iteration order.  Call right after
+    // construction or reinitialize() (the map must be empty).  Costs a few host round trips per frame.
+    void SetReferenceMapSemantics(bool on) { Check(sage_map_set_eviction(sage_pipeline_map(Handle()), on ? 1 : 0)); }
 
 private:
     static double *Data(Vector4dVector &v) { return v.empty() ? nullptr : v.front().data(); }

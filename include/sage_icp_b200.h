@@ -120,6 +120,12 @@ sage_map *sage_map_create(double voxel_size, double max_distance, int basic_poin
                           int critical_points_per_voxel, const int32_t *basic_parts_labels, int n_labels, int device);
 void sage_map_destroy(sage_map *m);
 int sage_map_clear(sage_map *m);                   /* VoxelHashMap::Clear  — core/VoxelHashMap.hpp:93 */
+/* Eviction / iteration-order mode (empty map only).  0 (default): RemovePointsFarFromLocation drops EVERY voxel whose first
+ * point is farther than max_distance, and dump/pointcloud come in device block order.  1: bucket-for-bucket emulation of the
+ * reference's erase-while-iterating sweep over its tsl::robin_map (core/VoxelHashMap.cpp:176-184 skips the element that
+ * backward-shift deletion moves into the erased bucket), and dump/pointcloud/LocalMap() in that map's iteration order
+ * (core/VoxelHashMap.cpp:132-142).  Mode 1 keeps a host mirror of the bucket array and adds host round trips per update. */
+int sage_map_set_eviction(sage_map *m, int faithful);
 int sage_map_empty(sage_map *m);                   /* VoxelHashMap::Empty  — core/VoxelHashMap.hpp:94 */
 int64_t sage_map_num_voxels(sage_map *m);
 int64_t sage_map_num_points(sage_map *m);
@@ -194,6 +200,13 @@ int64_t sage_launch_count(void);
  * order — core/Preprocessing.cpp:76-82 emits the down-sampled cloud in that order.  order_out[j] = input position of the
  * j-th element.  Pure host code (no device needed); exported so that it can be tested on its own. */
 int sage_robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out);
+
+/* Host mirror table behind sage_map_set_eviction(m, 1), exported so it can be tested without a device: replays n_ops records
+ * {op, x, y, z, r2} on an empty table — op 0 inserts voxel (x,y,z) (must be absent), op 1 runs the reference's
+ * erase-while-iterating sweep (core/VoxelHashMap.cpp:176-184) erasing every VISITED voxel whose integer squared distance from
+ * (x,y,z) exceeds r2, op 2 is clear().  Writes the surviving voxels in iteration (bucket) order to keys_out (3 ints each, at
+ * most cap voxels) and the bucket count to *bucket_count (may be NULL).  Returns the number of survivors, or < 0. */
+int64_t sage_robin_table_replay(const int32_t *ops, size_t n_ops, int32_t *keys_out, size_t cap, uint64_t *bucket_count);
 
 /* Query shard owned by `rank` out of `world` for n queries: contiguous [begin, end).  Pure host arithmetic. */
 int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end);

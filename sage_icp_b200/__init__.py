@@ -8,5 +8,5 @@ There is no CPU fallback: every entry point raises if the CUDA library or a B200
 from .config import SageConfig, launch_config  # noqa: F401
 from .capi import (  # noqa: F401
     SagePipeline, SageMap, SageError, build_library, library_path, load_library, device_count, launch_count,
-    shard_range, nccl_unique_id, robin_iteration_order,
+    shard_range, nccl_unique_id, robin_iteration_order, robin_table_replay,
 )

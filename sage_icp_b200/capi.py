@@ -117,6 +117,20 @@ def robin_iteration_order(hash20) -> np.ndarray:
     return out
 
 
+def robin_table_replay(ops):
+    """Host mirror table of the faithful-eviction mode (no device): ops = rows of (op, x, y, z, r2); returns (keys in
+    iteration order, bucket count)."""
+    L = load_library()
+    L.sage_robin_table_replay.restype = C.c_int64
+    o = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 5)
+    out = np.empty((len(o), 3), dtype=np.int32); bc = C.c_uint64(0)
+    ip = C.POINTER(C.c_int32)
+    k = L.sage_robin_table_replay(o.ctypes.data_as(ip), C.c_size_t(len(o)), out.ctypes.data_as(ip), C.c_size_t(len(o)), C.byref(bc))
+    if k < 0:
+        raise _err(L, "sage_robin_table_replay", int(k))
+    return out[:k].copy(), int(bc.value)
+
+
 def nccl_unique_id() -> bytes:
     L = load_library()
     buf = (C.c_uint8 * 128)()
@@ -155,6 +169,10 @@ class SageMap:
         return rc
 
     def clear(self): self._chk(self.L.sage_map_clear(self.h), "sage_map_clear")
+
+    def set_eviction(self, faithful: bool):
+        """True: the reference's erase-while-iterating eviction and robin_map iteration order (empty map only)."""
+        self._chk(self.L.sage_map_set_eviction(self.h, int(bool(faithful))), "sage_map_set_eviction")
     def empty(self) -> bool: return bool(self._chk(self.L.sage_map_empty(self.h), "sage_map_empty"))
     def num_voxels(self) -> int: return int(self._chk(self.L.sage_map_num_voxels(self.h), "sage_map_num_voxels"))
     def num_points(self) -> int: return int(self._chk(self.L.sage_map_num_points(self.h), "sage_map_num_points"))

@@ -211,6 +211,13 @@ int sage_map_clear(sage_map *m) {
         return 0;
     });
 }
+int sage_map_set_eviction(sage_map *m, int faithful) {
+    return (int)guarded([&] {
+        if (!m) throw ArgError("null argument");
+        m->impl->set_eviction_faithful(faithful != 0);
+        return 0;
+    });
+}
 int sage_map_empty(sage_map *m) {
     return (int)guarded([&] { return m->impl->empty() ? 1 : 0; });
 }
@@ -330,6 +337,40 @@ int sage_robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order
         if (n && (!hash20 || !order_out)) throw ArgError("null argument");
         robin_iteration_order(hash20, n, order_out);
         return 0;
+    });
+}
+int64_t sage_robin_table_replay(const int32_t *ops, size_t n_ops, int32_t *keys_out, size_t cap, uint64_t *bucket_count) {
+    return guarded([&]() -> int64_t {
+        if ((n_ops && !ops) || (cap && !keys_out)) throw ArgError("null argument");
+        HostVoxelTable t;
+        for (size_t i = 0; i < n_ops; ++i) {
+            const int32_t *o = ops + 5 * i;
+            if (o[0] == 0) {
+                if (!key_in_range(o[1], o[2], o[3])) throw ArgError("voxel key outside packable range");
+                const unsigned long long key = pack_key(o[1], o[2], o[3]);
+                t.insert(key, reference_voxel_hash(key), (uint32_t)i);
+            } else if (o[0] == 1) {
+                for (size_t b = 0; b < t.bucket_count(); ++b) {
+                    if (t.at(b).dist < 0) continue;
+                    int x, y, z;
+                    unpack_key(t.at(b).key, x, y, z);
+                    const long long dx = (long long)x - o[1], dy = (long long)y - o[2], dz = (long long)z - o[3];
+                    if (dx * dx + dy * dy + dz * dz > (long long)o[4]) t.erase_at(b);
+                }
+            } else if (o[0] == 2) {
+                t.clear();
+            } else {
+                throw ArgError("unknown op");
+            }
+        }
+        size_t k = 0;
+        for (size_t b = 0; b < t.bucket_count(); ++b) {
+            if (t.at(b).dist < 0) continue;
+            if (k < cap) unpack_key(t.at(b).key, keys_out[3 * k], keys_out[3 * k + 1], keys_out[3 * k + 2]);
+            ++k;
+        }
+        if (bucket_count) *bucket_count = t.bucket_count();
+        return (int64_t)k;
     });
 }
 int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end) {

@@ -9,6 +9,7 @@
 // The reference's sequential insert is order dependent only *within* a voxel, so voxels are replayed in parallel,
 // each by one thread walking its arrivals in input order (exact).
 #include <algorithm>
+#include <array>
 #include <cstring>
 
 #include "nccl_shim.cuh"
@@ -104,6 +105,7 @@ __global__ void map_insert_keys_kernel(MapView m, const double4 *in, double4 *pt
         m.blk_cnt[b] = 0;
         m.blk_head[b] = kNil;
         m.blk_slot[b] = s;
+        if (m.blk_new) m.blk_new[b] = 1, m.blk_first[b] = kNil;
         m.tbl[s].count = 0;
         m.tbl[s].block = b;
         atomicAdd(&m.ctrl->n_live, 1u);
@@ -208,6 +210,50 @@ __global__ void map_replay_kernel(MapView m, const double4 *pts, const uint32_t 
     m.blk_head[b] = kNil;
 }
 
+// ---- faithful-eviction mode: the host mirrors the reference's robin table, the device reports what it needs -------------
+// order in which this batch created voxels = order of their first point in the batch (core/VoxelHashMap.cpp:163-173)
+__global__ void map_mark_first_kernel(MapView m, const uint32_t *slot, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || slot[i] == kNil) return;
+    const uint32_t b = m.tbl[slot[i]].block;
+    if (m.blk_new[b]) atomicMin(m.blk_first + b, i);
+}
+__global__ void map_collect_new_kernel(MapView m, const uint32_t *slot, uint32_t n, uint32_t *out, uint32_t *count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || slot[i] == kNil) return;
+    const uint32_t b = m.tbl[slot[i]].block;
+    if (!m.blk_new[b] || m.blk_first[b] != i) return;
+    const uint32_t pos = atomicAdd(count, 1u);
+    const unsigned long long key = m.blk_key[b];
+    out[4 * pos] = i, out[4 * pos + 1] = b, out[4 * pos + 2] = (uint32_t)key, out[4 * pos + 3] = (uint32_t)(key >> 32);
+}
+__global__ void map_clear_new_kernel(MapView m, const uint32_t *list, const uint32_t *count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < *count) m.blk_new[list[4 * i + 1]] = 0;
+}
+__global__ void map_far_flags_kernel(MapView m, double ox, double oy, double oz, double max_d2, uint8_t *flags, uint32_t n_blocks) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    uint8_t far = 0;
+    if (b < m.ctrl->n_hi && m.blk_key[b] != kEmptyKey) {
+        const double4 f = m.blk_pts[(size_t)b * m.stride];  // voxel_block.points.front()
+        const double dx = __dsub_rn(f.x, ox), dy = __dsub_rn(f.y, oy), dz = __dsub_rn(f.z, oz);
+        far = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) > max_d2 ? 1 : 0;
+    }
+    flags[b] = far;
+}
+__global__ void map_evict_list_kernel(MapView m, const uint32_t *list, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = list[i];
+    m.blk_key[b] = kEmptyKey;
+    m.blk_cnt[b] = 0;
+    const int idx = atomicAdd(&m.ctrl->n_free, 1);
+    m.free_list[idx] = b;
+    atomicSub(&m.ctrl->n_live, 1u);
+    atomicAdd(&m.ctrl->evicted, 1u);
+}
+
 // RemovePointsFarFromLocation — core/VoxelHashMap.cpp:176-184, "clean" semantics (every far voxel goes)
 __global__ void map_evict_kernel(MapView m, double ox, double oy, double oz, double max_d2) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -294,6 +340,7 @@ MapView VoxelMapGPU::view() {
     MapView v;
     v.tbl = tbl_.p, v.mask = tbl_cap_ - 1;
     v.blk_key = blk_key_.p, v.blk_cnt = blk_cnt_.p, v.blk_head = blk_head_.p, v.blk_slot = blk_slot_.p, v.blk_pts = blk_pts_.p, v.blk_hot = blk_hot_.p;
+    v.blk_first = faithful_ ? blk_first_.p : nullptr, v.blk_new = faithful_ ? blk_new_.p : nullptr;
     v.free_list = free_list_.p, v.ctrl = ctrl_.p;
     v.stride = stride_, v.basic = basic_, v.critical = critical_;
     v.n_basic_labels = (int)basic_labels_.size();
@@ -313,6 +360,7 @@ void VoxelMapGPU::clear() {
     SAGE_LAUNCH(ctrl_set_kernel, 1, 1, 0, stream_, ctrl_.p, 0u, 0u);
     hi_bound_ = live_bound_ = 0;
     host_stats_ = MapCtrl{};
+    host_tbl_.clear();
 }
 
 void VoxelMapGPU::sync_stats() {
@@ -371,6 +419,12 @@ void VoxelMapGPU::reserve(size_t extra) {
         free_list_.ensure(want, stream_, true);
         blk_pts_.ensure(want * (size_t)stride_, stream_, true);
         blk_hot_.ensure(want * (size_t)stride_, stream_, true);
+        if (faithful_) {
+            const size_t old = blk_new_.cap;
+            blk_first_.ensure(want, stream_, true);
+            blk_new_.ensure(want, stream_, true);
+            SAGE_CUDA(cudaMemsetAsync(blk_new_.p + old, 0, blk_new_.cap - old, stream_));
+        }
         blk_cap_ = (uint32_t)std::min<size_t>({blk_key_.cap, blk_cnt_.cap, blk_head_.cap, blk_slot_.cap, free_list_.cap,
                                                 blk_pts_.cap / (size_t)stride_, blk_hot_.cap / (size_t)stride_});
     }
@@ -397,6 +451,7 @@ void VoxelMapGPU::add_points_dev(const double4 *pts, size_t n, const Pose *pose)
         SAGE_LAUNCH(map_replay_kernel, blocks_for(m), kThreads, 0, stream_, v, upd_pts_.p, upd_slot_.p, upd_next_.p, m);
         hi_bound_ += m;
         live_bound_ += m;
+        if (faithful_) record_new_voxels(m);
     }
 }
 
@@ -410,9 +465,162 @@ void VoxelMapGPU::add_points_host(const double *xyzl, size_t n, const Pose *pose
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// HostVoxelTable — published rules of tsl::robin_map v1.0.1 (power-of-two growth, robin-hood insertion, backward-shift erase)
+
+void HostVoxelTable::clear() {
+    for (auto &e : b_) e = Bucket{};
+    n_ = 0, grow_next_ = false;
+}
+
+// rehash placement: plain robin-hood walk from the ideal bucket, no growth bookkeeping
+void HostVoxelTable::place(std::vector<Bucket> &t, Bucket e, bool) {
+    const size_t mask = t.size() - 1;
+    size_t i = e.hash & mask;
+    for (int d = 0;; ++d, i = (i + 1) & mask) {
+        if (d <= t[i].dist) continue;
+        e.dist = d;
+        if (t[i].dist < 0) {
+            t[i] = e;
+            return;
+        }
+        std::swap(e, t[i]);
+        d = e.dist;
+    }
+}
+
+void HostVoxelTable::insert(unsigned long long key, uint32_t hash20, uint32_t block) {
+    constexpr int kDistLimit = 8192;  // DIST_FROM_IDEAL_BUCKET_LIMIT
+    size_t i = 0;
+    int d = 0;
+    auto walk = [&]() {  // the failed lookup that precedes every insert: stop where a resident is closer to home
+        const size_t mask = b_.size() - 1;
+        for (i = hash20 & mask, d = 0; d <= b_[i].dist; ++d) i = (i + 1) & mask;
+    };
+    if (!b_.empty()) walk();
+    // max_load_factor 0.5, growth x2 from 0 buckets; also the probe-length escape hatch (the 20-bit hash saturates)
+    while (grow_next_ || d > kDistLimit || n_ >= threshold_) {
+        // keys that agree on all 20 hash bits never separate: tsl would double until memory runs out; stop with an error instead
+        if (b_.size() >= ((size_t)1 << 27)) throw ArgError("robin_map mirror: unbounded growth (more than 8192 voxels on one hash value)");
+        std::vector<Bucket> bigger(b_.empty() ? 2 : b_.size() * 2);
+        for (const auto &e : b_)
+            if (e.dist >= 0) place(bigger, e, false);
+        b_.swap(bigger);
+        threshold_ = (size_t)((float)b_.size() * 0.5f);
+        grow_next_ = false;
+        walk();
+    }
+    const size_t mask = b_.size() - 1;
+    Bucket e;
+    e.hash = hash20, e.block = block, e.key = key, e.dist = d;
+    if (b_[i].dist >= 0) {
+        std::swap(e, b_[i]);
+        // carry the evicted resident forward; it displaces anyone closer to home than itself
+        for (d = e.dist + 1, i = (i + 1) & mask; b_[i].dist >= 0; ++d, i = (i + 1) & mask) {
+            if (d <= b_[i].dist) continue;
+            if (d >= kDistLimit) grow_next_ = true;
+            e.dist = d;
+            std::swap(e, b_[i]);
+            d = e.dist;
+        }
+        e.dist = d;
+    }
+    b_[i] = e;
+    ++n_;
+}
+
+void HostVoxelTable::erase_at(size_t i) {  // backward-shift deletion
+    const size_t mask = b_.size() - 1;
+    b_[i] = Bucket{};
+    --n_;
+    size_t prev = i, cur = (i + 1) & mask;
+    while (b_[cur].dist > 0) {
+        b_[prev] = b_[cur];
+        b_[prev].dist -= 1;
+        b_[cur] = Bucket{};
+        prev = cur, cur = (cur + 1) & mask;
+    }
+}
+
+uint32_t reference_voxel_hash(unsigned long long key) {  // core/VoxelHashMap.hpp:72-77
+    int x, y, z;
+    unpack_key(key, x, y, z);
+    return ((1u << 20) - 1u) & ((uint32_t)x * 73856093u ^ (uint32_t)y * 19349663u ^ (uint32_t)z * 83492791u);
+}
+
+void VoxelMapGPU::set_eviction_faithful(bool on) {
+    if (on == faithful_) return;
+    if (!empty()) throw ArgError("the eviction mode can only be changed on an empty map");
+    faithful_ = on;
+    host_tbl_ = HostVoxelTable{};
+    if (on && blk_cap_) {
+        blk_first_.ensure(blk_cap_);
+        blk_new_.ensure(blk_cap_);
+        SAGE_CUDA(cudaMemsetAsync(blk_new_.p, 0, blk_new_.cap, stream_));
+    }
+}
+
+// after a batch: the voxels it created, in the order the reference's sequential insert would have created them
+void VoxelMapGPU::record_new_voxels(uint32_t m) {
+    MapView v = view();
+    new_list_.ensure((size_t)4 * m + 4);
+    new_pin_.ensure((size_t)4 * m + 4);
+    uint32_t *count = new_list_.p + (size_t)4 * m;
+    SAGE_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), stream_));
+    SAGE_LAUNCH(map_mark_first_kernel, blocks_for(m), kThreads, 0, stream_, v, upd_slot_.p, m);
+    SAGE_LAUNCH(map_collect_new_kernel, blocks_for(m), kThreads, 0, stream_, v, upd_slot_.p, m, new_list_.p, count);
+    SAGE_LAUNCH(map_clear_new_kernel, blocks_for(m), kThreads, 0, stream_, v, new_list_.p, count);
+    SAGE_CUDA(cudaMemcpyAsync(new_pin_.p + (size_t)4 * m, count, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    const uint32_t k = new_pin_.p[(size_t)4 * m];
+    if (k == 0) return;
+    SAGE_CUDA(cudaMemcpyAsync(new_pin_.p, new_list_.p, (size_t)16 * k, cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    std::vector<std::array<uint32_t, 4>> created(k);
+    std::memcpy(created.data(), new_pin_.p, (size_t)16 * k);
+    std::sort(created.begin(), created.end(), [](const auto &a, const auto &b) { return a[0] < b[0]; });
+    for (const auto &c : created) {
+        const unsigned long long key = (unsigned long long)c[2] | ((unsigned long long)c[3] << 32);
+        host_tbl_.insert(key, reference_voxel_hash(key), c[1]);
+    }
+}
+
+// the reference's sweep: range-for over the robin_map, erase(key) inside; after an erase the iterator moves on from the
+// erased bucket, so the element shifted into it is not examined (core/VoxelHashMap.cpp:176-184)
+void VoxelMapGPU::remove_far_faithful(double ox, double oy, double oz) {
+    sync_stats();
+    const uint32_t n_blocks = host_stats_.n_hi;
+    if (n_blocks == 0) return;
+    far_flags_.ensure(n_blocks);
+    far_pin_.ensure(n_blocks);
+    MapView v = view();
+    SAGE_LAUNCH(map_far_flags_kernel, blocks_for(n_blocks), kThreads, 0, stream_, v, ox, oy, oz, max_distance_ * max_distance_, far_flags_.p, n_blocks);
+    SAGE_CUDA(cudaMemcpyAsync(far_pin_.p, far_flags_.p, n_blocks, cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    std::vector<uint32_t> gone;
+    for (size_t i = 0; i < host_tbl_.bucket_count(); ++i) {
+        const auto &e = host_tbl_.at(i);
+        if (e.dist >= 0 && far_pin_.p[e.block]) {
+            gone.push_back(e.block);
+            host_tbl_.erase_at(i);
+        }
+    }
+    if (gone.empty()) return;
+    evict_list_.ensure(gone.size());
+    evict_pin_.ensure(gone.size());
+    std::memcpy(evict_pin_.p, gone.data(), gone.size() * sizeof(uint32_t));
+    SAGE_CUDA(cudaMemcpyAsync(evict_list_.p, evict_pin_.p, gone.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+    SAGE_LAUNCH(map_evict_list_kernel, blocks_for(gone.size()), kThreads, 0, stream_, v, evict_list_.p, (uint32_t)gone.size());
+    SAGE_LAUNCH(tbl_clear_kernel, blocks_for(tbl_cap_), kThreads, 0, stream_, tbl_.p, tbl_cap_, ctrl_.p, 1);
+    SAGE_LAUNCH(tbl_reinsert_kernel, blocks_for(n_blocks), kThreads, 0, stream_, v, 1);
+    SAGE_LAUNCH(ctrl_finish_kernel, 1, 1, 0, stream_, ctrl_.p);
+    SAGE_CUDA(cudaStreamSynchronize(stream_));  // evict_pin_ may be refilled by the next call
+}
+
 void VoxelMapGPU::remove_far(double ox, double oy, double oz) {
     set_device();
     if (hi_bound_ == 0) return;
+    if (faithful_) return remove_far_faithful(ox, oy, oz);
     MapView v = view();
     SAGE_LAUNCH(map_evict_kernel, blocks_for(hi_bound_), kThreads, 0, stream_, v, ox, oy, oz, max_distance_ * max_distance_);
     SAGE_LAUNCH(tbl_clear_kernel, blocks_for(tbl_cap_), kThreads, 0, stream_, tbl_.p, tbl_cap_, ctrl_.p, 1);
@@ -435,8 +643,16 @@ long long VoxelMapGPU::dump(int32_t *keys, int32_t *counts, double *points, size
         SAGE_CUDA(cudaStreamSynchronize(stream_));
     }
     size_t v = 0;
-    for (size_t b = 0; b < hi; ++b) {
-        if (k[b] == kEmptyKey) continue;
+    // faithful mode: the reference's iteration order (bucket order of its robin_map); otherwise device block order
+    std::vector<size_t> order;
+    if (faithful_) {
+        for (size_t i = 0; i < host_tbl_.bucket_count(); ++i)
+            if (host_tbl_.at(i).dist >= 0) order.push_back(host_tbl_.at(i).block);
+    } else {
+        for (size_t b = 0; b < hi; ++b) order.push_back(b);
+    }
+    for (size_t b : order) {
+        if (b >= hi || k[b] == kEmptyKey) continue;
         int x, y, z;
         unpack_key(k[b], x, y, z);
         keys[3 * v] = x, keys[3 * v + 1] = y, keys[3 * v + 2] = z;
@@ -484,6 +700,8 @@ void VoxelMapGPU::load(const int32_t *keys, const int32_t *counts, const double 
     SAGE_CUDA(cudaMemsetAsync(blk_head_.p, 0xff, n_voxels * sizeof(uint32_t), stream_));
     SAGE_LAUNCH(ctrl_set_kernel, 1, 1, 0, stream_, ctrl_.p, (uint32_t)n_voxels, (uint32_t)n_voxels);
     hi_bound_ = live_bound_ = n_voxels;
+    if (faithful_)
+        for (size_t v = 0; v < n_voxels; ++v) host_tbl_.insert(k[v], reference_voxel_hash(k[v]), (uint32_t)v);
     SAGE_LAUNCH(map_build_hot_kernel, blocks_for(n_voxels * (size_t)stride_), kThreads, 0, stream_, view(), (uint32_t)n_voxels);
     rebuild_table(tbl_cap_);
     SAGE_CUDA(cudaStreamSynchronize(stream_));

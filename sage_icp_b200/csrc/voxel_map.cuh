@@ -21,6 +21,8 @@ struct MapView {
     double4 *blk_pts;    // [block][stride] x, y, z, label — bit-identical to Eigen::Vector4d ("cold" exact copy)
     float4 *blk_hot;     // [block][stride] 16-byte search record: f32 offsets from the voxel origin + label (see hot_record)
     uint32_t *free_list;
+    uint32_t *blk_first;  // faithful-eviction mode only (else null): smallest point index of the batch that created the block,
+    uint8_t *blk_new;     // and the "created by this batch" mark
     MapCtrl *ctrl;
     int stride;  // basic + critical
     int basic, critical;
@@ -28,6 +30,33 @@ struct MapView {
     int basic_labels[32];
     double voxel_size;
     uint32_t blk_cap;
+};
+
+// Host mirror of the reference's tsl::robin_map<Voxel, VoxelBlock, VoxelHash> as far as it is observable: which bucket
+// every voxel sits in.  Kept only in faithful-eviction mode, where RemovePointsFarFromLocation must reproduce the
+// erase-while-iterating sweep of core/VoxelHashMap.cpp:176-184 and LocalMap()/dump() the map's iteration order
+// (core/VoxelHashMap.cpp:132-142).  Same published rules as frontend.cu's replay, plus backward-shift erase.
+uint32_t reference_voxel_hash(unsigned long long packed_key);  // the reference's 20-bit VoxelHash of a packed key
+
+class HostVoxelTable {
+public:
+    struct Bucket {
+        int32_t dist = -1;  // -1 = empty
+        uint32_t hash = 0, block = 0;
+        unsigned long long key = 0;
+    };
+    void clear();  // tsl clear(): empties the buckets, keeps the bucket count
+    void insert(unsigned long long key, uint32_t hash20, uint32_t block);  // key must be absent
+    void erase_at(size_t i);
+    size_t bucket_count() const { return b_.size(); }
+    size_t size() const { return n_; }
+    const Bucket &at(size_t i) const { return b_[i]; }
+
+private:
+    void place(std::vector<Bucket> &t, Bucket e, bool track);
+    std::vector<Bucket> b_;
+    size_t n_ = 0, threshold_ = 0;
+    bool grow_next_ = false;
 };
 
 class VoxelMapGPU {
@@ -49,6 +78,10 @@ public:
         remove_far(pose.tx, pose.ty, pose.tz);
     }
     long long pointcloud(double *out, size_t cap_points);
+    // 0: every far voxel is evicted (default); 1: the reference's erase-while-iterating sweep, bucket for bucket.
+    // Only on an empty map.
+    void set_eviction_faithful(bool on);
+    bool eviction_faithful() const { return faithful_; }
     void load(const int32_t *keys, const int32_t *counts, const double *points, int stride, size_t n_voxels);
     long long dump(int32_t *keys, int32_t *counts, double *points, size_t cap_voxels);
 
@@ -119,6 +152,15 @@ private:
     // update scratch
     DevBuf<double4> upd_pts_;
     DevBuf<uint32_t> upd_slot_, upd_next_;
+    // faithful-eviction mode
+    bool faithful_ = false;
+    HostVoxelTable host_tbl_;
+    DevBuf<uint32_t> blk_first_, new_list_, evict_list_;
+    DevBuf<uint8_t> blk_new_, far_flags_;
+    PinBuf<uint32_t> new_pin_, evict_pin_;
+    PinBuf<uint8_t> far_pin_;
+    void record_new_voxels(uint32_t m);
+    void remove_far_faithful(double ox, double oy, double oz);
     // registration scratch
     DevBuf<double4> stage_, src_, tgt_;
     DevBuf<uint8_t> matched_;

@@ -143,3 +143,71 @@ def test_product_robin_replay_with_saturated_hash(lib, orc):
     got = sg.robin_iteration_order(h)
     want, _ = orc.robin_order(keys)
     assert np.array_equal(got.astype(np.int64), want)
+
+
+def _colliding_keys(n, hashes, seed):
+    """n distinct PACKABLE voxel keys (|coordinate| < 2^20) on the given values of the reference's 20-bit hash: for any (y, z)
+    one x mod 2^20 hits a given hash value, because the x multiplier is odd."""
+    rng = np.random.default_rng(seed)
+    inv = pow(73856093, -1, 1 << 20)
+    yz = np.unique(rng.integers(-500, 500, size=(2 * n, 2)), axis=0)
+    rng.shuffle(yz)
+    keys = []
+    for i, (y, z) in enumerate(yz[:n]):
+        target = hashes[i % len(hashes)]
+        rest = ((int(y) & 0xFFFFFFFF) * 19349663 ^ (int(z) & 0xFFFFFFFF) * 83492791) & 0xFFFFF
+        keys.append(((inv * (target ^ rest)) & 0xFFFFF, int(y), int(z)))
+    return np.array(keys, dtype=np.int32)
+
+
+@pytest.mark.parametrize("n,spread,seed", [(1, 3, 0), (40, 3, 1), (700, 8, 2), (5000, 25, 3)])
+def test_host_mirror_table_replay_matches_python_model(lib, n, spread, seed):
+    """The host mirror of the map's tsl::robin_map (faithful-eviction mode, csrc/voxel_map.cu HostVoxelTable): inserts, the
+    erase-while-iterating sweep and clear() against the pure-Python model of tests/test_oracle_robin.py, op for op."""
+    import sage_icp_b200 as sg
+    from test_oracle_robin import PyRobinMap, _hash
+    rng = np.random.default_rng(seed)
+    t, live, ops = PyRobinMap(), set(), []
+    origin = np.zeros(3, dtype=np.int64)
+    for rnd in range(6):
+        fresh = np.unique(rng.integers(-spread, spread + 1, size=(n, 3)) + origin, axis=0)
+        rng.shuffle(fresh)
+        for k in fresh:
+            k = tuple(int(v) for v in k)
+            if k in live:
+                continue
+            live.add(k)
+            t.insert(_hash(k), k)
+            ops.append((0, *k, 0))
+        r2 = int((0.8 * spread) ** 2) + 1
+        far = lambda k, o=origin.copy(): sum((a - int(b)) ** 2 for a, b in zip(k, o)) > r2
+        t.sweep(far)
+        ops.append((1, *[int(v) for v in origin], r2))
+        live = set(t.order())
+        if rnd == 3:
+            t.b = [None] * len(t.b)  # clear(): buckets emptied, bucket count kept
+            live = set()
+            ops.append((2, 0, 0, 0, 0))
+        keys, buckets = sg.robin_table_replay(ops)
+        assert [tuple(int(v) for v in k) for k in keys] == t.order(), rnd
+        assert buckets == len(t.b)
+        origin += rng.integers(0, spread // 2 + 2, 3)
+    assert len(sg.robin_table_replay(np.zeros((0, 5)))[0]) == 0
+    with pytest.raises(sg.SageError):
+        sg.robin_table_replay([(7, 0, 0, 0, 0)])
+
+
+@pytest.mark.parametrize("n,hashes", [(3000, list(range(7))), (8300, [77 + (j << 15) for j in range(32)])])
+def test_host_mirror_table_with_saturated_hash(lib, orc, n, hashes):
+    """Long probe sequences.  Second case: 8300 keys whose hashes agree in the low 15 bits collide on ONE bucket while the table
+    has <= 2^15 buckets, so the probe-length limit (8192) forces a growth the load factor alone would not ask for; compared with
+    the oracle's RobinTable (iteration order and bucket count).  (Keys on a single hash value would double forever — in tsl too.)"""
+    import sage_icp_b200 as sg
+    keys = _colliding_keys(n, hashes, 5)
+    assert set(orc.voxel_hash(*[int(v) for v in k]) for k in keys[:200]) <= set(hashes)
+    got, buckets = sg.robin_table_replay(np.c_[np.zeros(len(keys), np.int32), keys, np.zeros(len(keys), np.int32)])
+    want, want_buckets = orc.robin_order(keys)
+    assert np.array_equal(got, keys[want])
+    assert buckets == want_buckets
+    if len(hashes) == 32:
+        assert buckets == 2 * (1 << int(np.ceil(np.log2(2 * n - 1))))  # one doubling more than the load factor alone

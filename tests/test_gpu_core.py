@@ -73,6 +73,51 @@ def test_update_and_evict_clean_mode(orc):
     assert o.num_voxels() > 0
 
 
+def test_update_and_evict_faithful_mode(orc):
+    """sage_map_set_eviction(m, 1): the reference's erase-while-iterating sweep over its tsl::robin_map, bucket for bucket
+    (core/VoxelHashMap.cpp:176-184 leaves some far voxels behind), and the map's iteration order — the dump (voxel order,
+    stored points) and the exported cloud equal the oracle's in ORDER, frame after frame; far survivors really occur; blocks
+    freed by the sweep are reused; load() and clear() keep the mirror in step."""
+    g, o = _maps(orc, max_distance=30.0, faithful=True)
+    g.set_eviction(True)
+    clean, _ = _maps(orc, max_distance=30.0)
+    rng = np.random.default_rng(5)
+    leftovers = 0
+    for f in range(12):
+        pose = orc.se3_exp([4.0 * f, 0.3 * np.sin(f), 0.0, 0.0, 0.0, 0.02 * f])
+        local = np.empty((5000, 4))
+        local[:, :3] = rng.uniform(-25, 25, (5000, 3)) * np.array([1, 1, 0.1])
+        local[:, 3] = rng.choice([0, 40, 50, 80], 5000)
+        g.update(local, pose)
+        o.update(local, pose)
+        clean.update(local, pose)
+        gk, gc, gp = g.dump()
+        ok, oc, op = o.dump()
+        assert np.array_equal(gk, ok), f"frame {f}: voxel order"
+        assert np.array_equal(gc, oc) and np.array_equal(gp, op), f"frame {f}"
+        assert np.array_equal(g.pointcloud(), o.pointcloud()), f"frame {f}: Pointcloud() order"
+        leftovers += g.num_voxels() - clean.num_voxels()
+    assert leftovers > 0  # the faithful sweep kept voxels the clean one dropped
+    # queries see the left-over far voxels exactly as the reference would
+    q = np.c_[rng.uniform(-60, 60, (4000, 2)) + [44.0, 0.0], rng.uniform(-2, 2, 4000), rng.choice([0, 40, 50, 80], 4000).astype(float)]
+    tg, mg = g.get_correspondences(q, 2.0, 0.4)
+    src, tgt, qi = o.get_correspondences(q, 2.0, 0.4)
+    assert np.array_equal(np.flatnonzero(mg), qi) and np.array_equal(tg[mg], tgt)
+    # a snapshot loaded into a faithful map takes the snapshot's order as insertion order, like re-inserting it would
+    g2, o2 = _maps(orc, max_distance=30.0, faithful=True)
+    g2.set_eviction(True)
+    g2.load(*o.dump())
+    for k, c, p in zip(*o.dump()):
+        o2.add_points(p[:c])
+    assert np.array_equal(g2.dump()[0], o2.dump()[0])
+    import sage_icp_b200 as sg
+    with pytest.raises(sg.SageError):
+        g.set_eviction(False)  # only on an empty map
+    g.clear(); o.clear()
+    g.update(local, pose); o.update(local, pose)
+    assert np.array_equal(g.dump()[0], o.dump()[0])  # clear() keeps the bucket count, on both sides
+
+
 def test_empty_inputs(orc):
     g, o = _maps(orc)
     assert g.empty() and g.num_voxels() == 0 and g.num_points() == 0

@@ -62,3 +62,41 @@ def test_deskewed_drive_parity(orc):
         assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (i, dt, da)
         assert np.allclose(gp.last_source(), op.last_source(), atol=1e-9), i  # de-skewed points differ at rounding level only
     assert len(gp.poses()) == 12
+
+
+def test_streaming_drive_with_the_reference_eviction_quirk(orc):
+    """The same kind of drive with sage_map_set_eviction(map, 1) against the oracle in ITS faithful mode: the far voxels the
+    reference's erase-while-iterating sweep leaves behind stay searchable on both sides, so poses, iteration counts and the
+    map agree frame by frame — and LocalMap() comes out in the reference's order (tsl::robin_map iteration order)."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config(local_map_range=30.0)
+    gp, op = sg.SagePipeline(cfg), orc.OraclePipeline(cfg, threads=orc.max_threads(), evict_faithful=True)
+    gp.map().set_eviction(True)
+    clean = sg.SagePipeline(cfg)
+    n = 60
+    traj = syn.trajectory(n)
+    extra = 0
+    for i in range(n):
+        scan = syn.make_scan(4000 + i, tuple(traj[i]), n_beams=32, n_az=1200)
+        pg, _, _ = gp.register_frame(scan)
+        po, _, _ = op.register_frame(scan)
+        clean.register_frame(scan)
+        dt, da = pose_delta(pg, po)
+        assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (i, dt, da)
+        assert gp.last_iterations() == op.last_iterations(), i
+        if i % 6 == 5:
+            gk, gc, gpts = gp.map().dump()
+            ok, oc, opts = op.map().dump()
+            assert np.array_equal(gk, ok) and np.array_equal(gc, oc), i  # same voxels in the same (robin) order
+            assert np.allclose(gpts, opts, atol=1e-7, rtol=0)
+            extra = max(extra, gp.map().num_voxels() - clean.map().num_voxels())
+    assert extra > 0  # the quirk was exercised: voxels a clean sweep would have dropped are still in the map
+    a, b = gp.local_map(), op.local_map()
+    assert a.shape == b.shape and np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a, b, atol=1e-7, rtol=0)
+    gp.reinitialize(); op.reset()
+    assert gp.map().empty()
+    scan = syn.make_scan(4000, tuple(traj[0]), n_beams=32, n_az=1200)
+    gp.register_frame(scan); op.register_frame(scan)
+    assert np.array_equal(gp.map().dump()[0], op.map().dump()[0])  # Clear() kept the bucket count on both sides

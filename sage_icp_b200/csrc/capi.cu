@@ -38,6 +38,19 @@ static long long guarded(F &&f) {
     }
 }
 
+// every entry point goes through these: a NULL handle is an error code, never a crash
+static Pipeline &P(sage_pipeline *h) {
+    if (!h || !h->impl) throw ArgError("null pipeline handle");
+    return *h->impl;
+}
+static VoxelMapGPU &M(sage_map *m) {
+    if (!m || !m->impl) throw ArgError("null map handle");
+    return *m->impl;
+}
+static void need(const void *p, const char *what) {
+    if (!p) throw ArgError(std::string("null argument: ") + what);
+}
+
 static long long copy_out(const std::vector<double> &v, double *out, size_t cap_points) {
     const size_t n = v.size() / 4;
     if (!out) return (long long)n;
@@ -85,17 +98,18 @@ void sage_destroy(sage_pipeline *h) {
 }
 int sage_reset(sage_pipeline *h) {
     return (int)guarded([&] {
-        h->impl->reinitialize();
+        P(h).reinitialize();
         return 0;
     });
 }
 int sage_register_frame(sage_pipeline *h, const double *xyzl, size_t n, const double *timestamps, double pose_out[7], double *t_icp,
                         double *t_all) {
     return (int)guarded([&] {
-        if (!h || (!xyzl && n)) throw ArgError("null argument");
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
+        need(pose_out, "pose_out");
         Pose p;
         double ti = 0, ta = 0;
-        h->impl->register_frame(xyzl, n, timestamps, p, ti, ta);
+        P(h).register_frame(xyzl, n, timestamps, p, ti, ta);
         pose_to_wire(p, pose_out);
         if (t_icp) *t_icp = ti;
         if (t_all) *t_all = ta;
@@ -106,11 +120,12 @@ int sage_register_frame_pointcloud2(sage_pipeline *h, const uint8_t *data, size_
                                     uint32_t y_offset, uint32_t z_offset, uint32_t label_offset, int label_datatype, const double *timestamps,
                                     double pose_out[7], double *t_icp, double *t_all) {
     return (int)guarded([&] {
-        if (!h || (!data && n_points)) throw ArgError("null argument");
+        if (!data && n_points) throw ArgError("null argument: data");
+        need(pose_out, "pose_out");
         if (label_datatype != 2 && label_datatype != 7) throw ArgError("label_datatype must be 2 (UINT8) or 7 (FLOAT32)");
         Pose p;
         double ti = 0, ta = 0;
-        h->impl->register_frame_pointcloud2(data, n_points, point_step, x_offset, y_offset, z_offset, label_offset, label_datatype == 7,
+        P(h).register_frame_pointcloud2(data, n_points, point_step, x_offset, y_offset, z_offset, label_offset, label_datatype == 7,
                                             timestamps, p, ti, ta);
         pose_to_wire(p, pose_out);
         if (t_icp) *t_icp = ti;
@@ -120,41 +135,62 @@ int sage_register_frame_pointcloud2(sage_pipeline *h, const uint8_t *data, size_
 }
 int64_t sage_last_source(sage_pipeline *h, double *out, size_t cap) {
     return guarded([&] {
-        if (!out) return (long long)h->impl->n_source();
-        h->impl->last_source(h->scratch);
+        if (!out) return (long long)P(h).n_source();
+        P(h).last_source(h->scratch);
         return copy_out(h->scratch, out, cap);
     });
 }
 int64_t sage_last_frame_downsample(sage_pipeline *h, double *out, size_t cap) {
     return guarded([&] {
-        if (!out) return (long long)h->impl->n_downsample();
-        h->impl->last_downsample(h->scratch);
+        if (!out) return (long long)P(h).n_downsample();
+        P(h).last_downsample(h->scratch);
         return copy_out(h->scratch, out, cap);
     });
 }
-int sage_last_iterations(sage_pipeline *h) { return h->impl->last_iterations(); }
-double sage_last_sigma(sage_pipeline *h) { return h->impl->last_sigma(); }
+int sage_last_iterations(sage_pipeline *h) {
+    return (int)guarded([&] { return P(h).last_iterations(); });
+}
+double sage_last_sigma(sage_pipeline *h) {
+    double v = -1.0;
+    guarded([&] { return v = P(h).last_sigma(), 0; });
+    return v;
+}
 
 int sage_voxelize(sage_pipeline *h, const double *xyzl, size_t n, double *source_out, size_t *n_source, double *downsample_out,
                   size_t *n_downsample) {
     return (int)guarded([&] {
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
+        need(n_source, "n_source"), need(n_downsample, "n_downsample");
         std::vector<double> s, d;
-        h->impl->voxelize_host(xyzl, n, s, d);
+        P(h).voxelize_host(xyzl, n, s, d);
         *n_source = s.size() / 4, *n_downsample = d.size() / 4;
         if (source_out && !s.empty()) std::memcpy(source_out, s.data(), s.size() * sizeof(double));
         if (downsample_out && !d.empty()) std::memcpy(downsample_out, d.data(), d.size() * sizeof(double));
         return 0;
     });
 }
-double sage_get_adaptive_threshold(sage_pipeline *h) { return h->impl->get_adaptive_threshold(); }
-int sage_has_moved(sage_pipeline *h) { return h->impl->has_moved() ? 1 : 0; }
+double sage_get_adaptive_threshold(sage_pipeline *h) {
+    double v = -1.0;
+    guarded([&] { return v = P(h).get_adaptive_threshold(), 0; });
+    return v;
+}
+int sage_has_moved(sage_pipeline *h) {
+    return (int)guarded([&] { return P(h).has_moved() ? 1 : 0; });
+}
 int sage_get_prediction_model(sage_pipeline *h, double pose_out[7]) {
-    pose_to_wire(h->impl->get_prediction_model(), pose_out);
-    return 0;
+    return (int)guarded([&] {
+        need(pose_out, "pose_out");
+        pose_to_wire(P(h).get_prediction_model(), pose_out);
+        return 0;
+    });
 }
 int sage_transform_to_last_frame(sage_pipeline *h, const double last_pose[7], const double current_pose[7], const double *xyzl, size_t n,
                                  double *out) {
     (void)h;
+    if (!last_pose || !current_pose || (n && (!xyzl || !out))) {
+        g_err = "null argument";
+        return SAGE_EINVAL;
+    }
     // TransformPoints(last_pose.inverse() * current_pose, points): a few thousand points for RViz; host arithmetic
     const Pose T = pose_mul(pose_inverse(pose_from_wire(last_pose)), pose_from_wire(current_pose));
     for (size_t i = 0; i < n; ++i) {
@@ -165,28 +201,32 @@ int sage_transform_to_last_frame(sage_pipeline *h, const double last_pose[7], co
     }
     return 0;
 }
-int64_t sage_num_poses(sage_pipeline *h) { return (int64_t)h->impl->poses().size(); }
+int64_t sage_num_poses(sage_pipeline *h) {
+    return guarded([&] { return (long long)P(h).poses().size(); });
+}
 int sage_get_pose(sage_pipeline *h, size_t i, double pose_out[7]) {
-    if (i >= h->impl->poses().size()) {
-        g_err = "pose index out of range";
-        return SAGE_EINVAL;
-    }
-    pose_to_wire(h->impl->poses()[i], pose_out);
-    return 0;
+    return (int)guarded([&] {
+        need(pose_out, "pose_out");
+        if (i >= P(h).poses().size()) throw ArgError("pose index out of range");
+        pose_to_wire(P(h).poses()[i], pose_out);
+        return 0;
+    });
 }
 int64_t sage_local_map(sage_pipeline *h, double *out, size_t cap) {
-    return guarded([&] { return h->impl->map().pointcloud(out, cap); });
+    return guarded([&] { return P(h).map().pointcloud(out, cap); });
 }
-sage_map *sage_pipeline_map(sage_pipeline *h) { return &h->map_handle; }
+sage_map *sage_pipeline_map(sage_pipeline *h) { return h ? &h->map_handle : nullptr; }
 int64_t sage_preprocess(sage_pipeline *h, const double *xyzl, size_t n, double *out, size_t cap) {
     return guarded([&] {
-        h->impl->preprocess_host(xyzl, n, h->scratch);
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
+        P(h).preprocess_host(xyzl, n, h->scratch);
         return copy_out(h->scratch, out, cap);
     });
 }
 int64_t sage_voxel_downsample(sage_pipeline *h, const double *xyzl, size_t n, double vox_scale, double *out, size_t cap) {
     return guarded([&] {
-        h->impl->downsample_host(xyzl, n, vox_scale, h->scratch);
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
+        P(h).downsample_host(xyzl, n, vox_scale, h->scratch);
         return copy_out(h->scratch, out, cap);
     });
 }
@@ -207,66 +247,76 @@ void sage_map_destroy(sage_map *m) {
 }
 int sage_map_clear(sage_map *m) {
     return (int)guarded([&] {
-        m->impl->clear();
+        M(m).clear();
         return 0;
     });
 }
 int sage_map_set_eviction(sage_map *m, int faithful) {
     return (int)guarded([&] {
         if (!m) throw ArgError("null argument");
-        m->impl->set_eviction_faithful(faithful != 0);
+        M(m).set_eviction_faithful(faithful != 0);
         return 0;
     });
 }
 int sage_map_empty(sage_map *m) {
-    return (int)guarded([&] { return m->impl->empty() ? 1 : 0; });
+    return (int)guarded([&] { return M(m).empty() ? 1 : 0; });
 }
 int64_t sage_map_num_voxels(sage_map *m) {
-    return guarded([&] { return m->impl->num_voxels(); });
+    return guarded([&] { return M(m).num_voxels(); });
 }
 int64_t sage_map_num_points(sage_map *m) {
-    return guarded([&] { return m->impl->num_points(); });
+    return guarded([&] { return M(m).num_points(); });
 }
 int sage_map_add_points(sage_map *m, const double *xyzl, size_t n) {
     return (int)guarded([&] {
-        m->impl->add_points_host(xyzl, n, nullptr);
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
+        M(m).add_points_host(xyzl, n, nullptr);
         return 0;
     });
 }
 int sage_map_remove_far(sage_map *m, const double origin[3]) {
     return (int)guarded([&] {
-        m->impl->remove_far(origin[0], origin[1], origin[2]);
+        need(origin, "origin");
+        M(m).remove_far(origin[0], origin[1], origin[2]);
         return 0;
     });
 }
 int sage_map_update(sage_map *m, const double *xyzl, size_t n, const double pose[7]) {
     return (int)guarded([&] {
+        need(pose, "pose");
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
         const Pose T = pose_from_wire(pose);
-        m->impl->add_points_host(xyzl, n, &T);
-        m->impl->remove_far(T.tx, T.ty, T.tz);
+        M(m).add_points_host(xyzl, n, &T);
+        M(m).remove_far(T.tx, T.ty, T.tz);
         return 0;
     });
 }
 int64_t sage_map_pointcloud(sage_map *m, double *out, size_t cap) {
-    return guarded([&] { return m->impl->pointcloud(out, cap); });
+    return guarded([&] { return M(m).pointcloud(out, cap); });
 }
 int sage_map_load(sage_map *m, const int32_t *keys, const int32_t *counts, const double *points, int stride, size_t n_voxels) {
     return (int)guarded([&] {
-        m->impl->load(keys, counts, points, stride, n_voxels);
+        if (n_voxels) need(keys, "keys"), need(counts, "counts"), need(points, "points");
+        M(m).load(keys, counts, points, stride, n_voxels);
         return 0;
     });
 }
 int64_t sage_map_dump(sage_map *m, int32_t *keys, int32_t *counts, double *points, size_t cap_voxels) {
-    return guarded([&] { return m->impl->dump(keys, counts, points, cap_voxels); });
+    return guarded([&] { return M(m).dump(keys, counts, points, cap_voxels); });
 }
 int64_t sage_map_get_correspondences(sage_map *m, const double *xyzl, size_t n, double max_dist, double th, double *target_out,
                                      uint8_t *matched_out) {
-    return guarded([&] { return m->impl->get_correspondences(xyzl, n, max_dist, th, target_out, matched_out); });
+    return guarded([&] {
+        if (n) need(xyzl, "xyzl"), need(target_out, "target_out"), need(matched_out, "matched_out");
+        return M(m).get_correspondences(xyzl, n, max_dist, th, target_out, matched_out);
+    });
 }
 int sage_map_nn_stats(sage_map *m, const double *xyzl, size_t n, uint64_t *occupied, uint64_t *candidates) {
     return (int)guarded([&] {
+        need(occupied, "occupied"), need(candidates, "candidates");
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
         unsigned long long o = 0, c = 0;
-        m->impl->nn_stats(xyzl, n, &o, &c);
+        M(m).nn_stats(xyzl, n, &o, &c);
         *occupied = o, *candidates = c;
         return 0;
     });
@@ -274,8 +324,10 @@ int sage_map_nn_stats(sage_map *m, const double *xyzl, size_t n, uint64_t *occup
 int sage_map_search_work(sage_map *m, const double *xyzl, size_t n, double max_dist, double th, uint64_t *scanned, uint64_t *probes,
                          uint64_t *exact, uint64_t *deferred) {
     return (int)guarded([&] {
+        need(scanned, "scanned"), need(probes, "probes"), need(exact, "exact");
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
         unsigned long long a = 0, b = 0, c = 0, d = 0;
-        m->impl->search_work(xyzl, n, max_dist, th, &a, &b, &c, &d);
+        M(m).search_work(xyzl, n, max_dist, th, &a, &b, &c, &d);
         *scanned = a, *probes = b, *exact = c;
         if (deferred) *deferred = d;
         return 0;
@@ -284,8 +336,10 @@ int sage_map_search_work(sage_map *m, const double *xyzl, size_t n, double max_d
 int sage_core_register_frame(sage_map *m, const double *frame, size_t n, const double guess[7], double max_dist, double kernel,
                              double sem_th, int max_iters, double est_th, double pose_out[7], int *iters_out) {
     return (int)guarded([&] {
+        need(guess, "guess"), need(pose_out, "pose_out");
+        if (!frame && n) throw ArgError("null argument: frame");
         Pose out;
-        const int it = m->impl->register_frame_host(frame, n, pose_from_wire(guess), max_dist, kernel, sem_th, max_iters, est_th, out);
+        const int it = M(m).register_frame_host(frame, n, pose_from_wire(guess), max_dist, kernel, sem_th, max_iters, est_th, out);
         pose_to_wire(out, pose_out);
         if (iters_out) *iters_out = it;
         return 0;
@@ -294,8 +348,10 @@ int sage_core_register_frame(sage_map *m, const double *frame, size_t n, const d
 int sage_core_register_frame_device(sage_map *m, const void *frame_dev, size_t n, const double guess[7], double max_dist, double kernel,
                                     double sem_th, int max_iters, double est_th, double pose_out[7], int *iters_out) {
     return (int)guarded([&] {
+        need(guess, "guess"), need(pose_out, "pose_out");
+        if (!frame_dev && n) throw ArgError("null argument: frame_dev");
         Pose out;
-        const int it = m->impl->register_frame_dev((const double4 *)frame_dev, n, pose_from_wire(guess), max_dist, kernel, sem_th,
+        const int it = M(m).register_frame_dev((const double4 *)frame_dev, n, pose_from_wire(guess), max_dist, kernel, sem_th,
                                                    max_iters, est_th, out);
         pose_to_wire(out, pose_out);
         if (iters_out) *iters_out = it;
@@ -305,31 +361,38 @@ int sage_core_register_frame_device(sage_map *m, const void *frame_dev, size_t n
 int sage_core_normal_equations(sage_map *m, const double *frame, size_t n, double max_dist, double kernel, double sem_th,
                                double JTJ[36], double JTr[6], int64_t *pairs) {
     return (int)guarded([&] {
+        need(JTJ, "JTJ"), need(JTr, "JTr");
+        if (!frame && n) throw ArgError("null argument: frame");
         long long np = 0;
-        m->impl->normal_equations(frame, n, max_dist, kernel, sem_th, JTJ, JTr, &np);
+        M(m).normal_equations(frame, n, max_dist, kernel, sem_th, JTJ, JTr, &np);
         if (pairs) *pairs = np;
         return 0;
     });
 }
 
 // ---- measurement / multi-GPU ------------------------------------------------------------------
-void *sage_map_stream(sage_map *m) { return (void *)m->impl->stream(); }
+void *sage_map_stream(sage_map *m) { return m && m->impl ? (void *)m->impl->stream() : nullptr; }
 int sage_map_profile_enable(sage_map *m, int enable) {
-    m->impl->profile_enable(enable != 0);
-    return 0;
+    return (int)guarded([&] {
+        M(m).profile_enable(enable != 0);
+        return 0;
+    });
 }
 int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms) {
     return (int)guarded([&] {
         long long l = 0;
         double ms = 0;
-        m->impl->profile_read(&l, &ms);
+        M(m).profile_read(&l, &ms);
         if (launches) *launches = l;
         if (total_ms) *total_ms = ms;
         return 0;
     });
 }
 // development aid, deliberately not in the public header
-size_t sage_debug_timeline(sage_map *m, unsigned long long *out, size_t cap) { return m->impl->debug_timeline(out, cap); }
+size_t sage_debug_timeline(sage_map *m, unsigned long long *out, size_t cap) {
+    const long long rc = guarded([&] { return (long long)M(m).debug_timeline(out, cap); });
+    return rc < 0 ? 0 : (size_t)rc;
+}
 int64_t sage_launch_count(void) { return g_launches.load(); }
 
 int sage_robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out) {
@@ -385,32 +448,37 @@ int sage_shard_range(size_t n, int rank, int world, size_t *begin, size_t *end) 
 }
 int sage_nccl_unique_id(uint8_t id_out[128]) {
     return (int)guarded([&] {
+        need(id_out, "id_out");
         nccl_unique_id(id_out);
         return 0;
     });
 }
 int sage_map_comm_init(sage_map *m, int rank, int world, const uint8_t id[128]) {
     return (int)guarded([&] {
-        m->impl->comm_init(rank, world, id);
+        need(id, "id");
+        if (world < 1 || rank < 0 || rank >= world) throw ArgError("bad rank / world");
+        M(m).comm_init(rank, world, id);
         return 0;
     });
 }
 int sage_map_comm_peer_handle(sage_map *m, uint8_t handle_out[64]) {
     return (int)guarded([&] {
-        m->impl->peer_handle(handle_out);
+        need(handle_out, "handle_out");
+        M(m).peer_handle(handle_out);
         return 0;
     });
 }
 int sage_map_comm_peer_attach(sage_map *m, int rank, int world, const uint8_t *handles) {
     return (int)guarded([&] {
-        m->impl->peer_attach(rank, world, handles);
+        need(handles, "handles");
+        M(m).peer_attach(rank, world, handles);
         return 0;
     });
 }
 int sage_map_comm_destroy(sage_map *m) {
     return (int)guarded([&] {
-        m->impl->comm_destroy();
-        m->impl->peer_detach();
+        M(m).comm_destroy();
+        M(m).peer_detach();
         return 0;
     });
 }

@@ -211,3 +211,27 @@ def test_host_mirror_table_with_saturated_hash(lib, orc, n, hashes):
     assert buckets == want_buckets
     if len(hashes) == 32:
         assert buckets == 2 * (1 << int(np.ceil(np.log2(2 * n - 1))))  # one doubling more than the load factor alone
+
+
+def test_null_handles_are_error_codes_not_crashes(lib):
+    """Every entry point checks its handle: a NULL pipeline / map gives a negative code and a message."""
+    L = lib
+    d7 = (C.c_double * 7)()
+    null = C.c_void_p(None)
+    for name, args in [("sage_reset", ()), ("sage_last_iterations", ()), ("sage_has_moved", ()), ("sage_get_prediction_model", (d7,)),
+                       ("sage_get_pose", (C.c_size_t(0), d7)), ("sage_register_frame", (None, C.c_size_t(0), None, d7, None, None))]:
+        rc = getattr(L, name)(null, *args)
+        assert rc < 0, name
+        assert b"null" in L.sage_last_error(), name
+    for name, args in [("sage_map_clear", ()), ("sage_map_empty", ()), ("sage_map_set_eviction", (1,)), ("sage_map_remove_far", (d7,)),
+                       ("sage_map_add_points", (None, C.c_size_t(0))), ("sage_map_comm_destroy", ()), ("sage_map_profile_enable", (1,))]:
+        rc = getattr(L, name)(null, *args)
+        assert rc < 0, name
+        assert b"null" in L.sage_last_error(), name
+    L.sage_num_poses.restype = C.c_int64
+    L.sage_local_map.restype = C.c_int64
+    assert L.sage_num_poses(null) < 0 and L.sage_local_map(null, None, C.c_size_t(0)) < 0
+    L.sage_pipeline_map.restype = C.c_void_p
+    L.sage_map_stream.restype = C.c_void_p
+    assert L.sage_pipeline_map(null) is None and L.sage_map_stream(null) is None
+    L.sage_destroy(null); L.sage_map_destroy(null)  # no-ops

@@ -11,12 +11,15 @@ namespace sage {
 static GroupTable make_groups(const sage_config_pod &c) {
     if (c.n_groups < 1) throw ArgError("sageConfig needs at least one voxel group (voxel_labels / voxel_size)");
     if (c.n_groups > kMaxGroups) throw ArgError("at most 16 voxel groups supported");
+    if (!c.voxel_size || !c.group_offsets || !c.group_labels) throw ArgError("sageConfig: voxel_size / group_offsets / group_labels is NULL");
+    if (c.group_offsets[0] != 0) throw ArgError("group_offsets must start at 0");
     GroupTable g{};
     g.n_groups = c.n_groups;
     g.n_labels = 0;
     for (int i = 0; i < c.n_groups; ++i) {
         g.voxel_size[i] = c.voxel_size[i];
         if (!(c.voxel_size[i] > 0)) throw ArgError("voxel_size must be positive");
+        if (c.group_offsets[i + 1] < c.group_offsets[i]) throw ArgError("group_offsets must be non-decreasing");
         for (int k = c.group_offsets[i]; k < c.group_offsets[i + 1]; ++k) {
             if (g.n_labels >= kMaxGroupLabels) throw ArgError("at most 64 labels across voxel groups supported");
             g.label[g.n_labels] = c.group_labels[k];

@@ -301,10 +301,15 @@ __global__ void ctrl_set_kernel(MapCtrl *ctrl, uint32_t n_hi, uint32_t n_live) {
 // ---------------------------------------------------------------------------------------------
 // host class
 
+static std::vector<int32_t> checked_labels(const int32_t *labels, int n) {
+    if (n < 0 || (n > 0 && !labels)) throw ArgError("basic_parts_labels is NULL or its length negative");
+    return n ? std::vector<int32_t>(labels, labels + n) : std::vector<int32_t>();
+}
+
 VoxelMapGPU::VoxelMapGPU(double voxel_size, double max_distance, int basic, int critical, const int32_t *labels, int n_labels,
                          int device)
     : voxel_size_(voxel_size), max_distance_(max_distance), basic_(basic), critical_(critical), stride_(basic + critical),
-      basic_labels_(labels, labels + n_labels), device_(device) {
+      basic_labels_(checked_labels(labels, n_labels)), device_(device) {
     if (!(voxel_size > 0) || basic < 0 || critical < 0 || basic + critical < 1) throw ArgError("bad voxel map parameters");
     if (n_labels > 32) throw ArgError("at most 32 basic_parts_labels supported");
     int count = 0;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# scratch: new faithful-eviction tests first, then the map/pipeline regression subset
+# scratch: staged-scan experiment
 mkdir -p gpurun_out
-timeout 240 python -m pytest tests/test_gpu_core.py::test_update_and_evict_faithful_mode tests/test_gpu_streaming.py::test_streaming_drive_with_the_reference_eviction_quirk -x -q -m gpu --timeout 200 --timeout-method=thread 2>&1 | tail -30 | tee gpurun_out/quick_faithful.log
-timeout 300 python -m pytest tests/test_gpu_core.py tests/test_gpu_pipeline.py -x -q -m gpu --timeout 120 --timeout-method=thread 2>&1 | tail -8 | tee gpurun_out/quick_regress.log
+timeout 200 python tools/stage_probe.py 0,16,40,8 2>&1 | tail -12 | tee gpurun_out/stage_probe.log
+SAGE_STAGE_CAP=16 timeout 200 python -m pytest tests/test_gpu_search_exactness.py tests/test_gpu_core.py -x -q -m gpu --timeout 120 --timeout-method=thread 2>&1 | tail -5 | tee gpurun_out/stage_parity16.log

@@ -19,6 +19,8 @@
 //      the queries) the query is re-ranked by nn_exact(): the reference's own f64 operation sequence over all 27 voxels in
 //      enumeration order with the strict-'<' first-wins rule (core/VoxelHashMap.cpp:57-63,81-93).
 //   5. The winner's exact f64 record is fetched for the acceptance test and the residual.
+#include <cooperative_groups.h>
+
 #include <cfloat>
 #include <cstdlib>
 
@@ -136,6 +138,12 @@ __device__ __noinline__ void icp_solve_xi(const double *S, double xi[6]) {
     xi[0] = (btx - (oy * z - oz * y)) * iw, xi[1] = (bty - (oz * x - ox * z)) * iw, xi[2] = (btz - (ox * y - oy * x)) * iw;
     xi[3] = ox, xi[4] = oy, xi[5] = oz;
 }
+// IcpState fields that change from one iteration to the next are read past L1 (ld.global.cg): in the persistent kernel the
+// block that takes the step is a different one every iteration, on an SM whose L1 may still hold the line from an earlier turn.
+__device__ __forceinline__ Pose load_pose_cg(const Pose *q) {
+    const double *d = reinterpret_cast<const double *>(q);
+    return Pose{__ldcg(d), __ldcg(d + 1), __ldcg(d + 2), __ldcg(d + 3), __ldcg(d + 4), __ldcg(d + 5), __ldcg(d + 6)};
+}
 __device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
     if (threadIdx.x == 0) {
         double xi[6];
@@ -148,10 +156,10 @@ __device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, doubl
     if (threadIdx.x == 0) {
         const Pose est = *s_pose;
         st->est = est;
-        const Pose T = pose_mul(est, st->T_icp);
+        const Pose T = pose_mul(est, load_pose_cg(&st->T_icp));
         st->T_icp = T;
         st->result = pose_mul(T, st->guess);  // only read once done
-        st->iter += 1;
+        st->iter = __ldcg(&st->iter) + 1;
     } else if (threadIdx.x == 32) {
         double lg[6];
         pose_log(*s_pose, lg);
@@ -163,7 +171,7 @@ __device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, doubl
     __syncthreads();
     if (threadIdx.x == 0) {
         st->last_norm = *s_norm;
-        if (*s_norm < st->est_th || st->iter >= st->max_iters) st->done = 1;
+        if (*s_norm < st->est_th || __ldcg(&st->iter) >= st->max_iters) st->done = 1;
     }
 }
 
@@ -452,7 +460,7 @@ __device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s
 // cross-section of the scan and the expensive regions (sparse, far from the sensor) spread over all SMs.
 #define SAGE_STAMP(i) do { if (p.dbg && pass == 0 && warp == 0) { __syncwarp(); if (lane == 0) p.dbg[kDbg * blockIdx.x + (i)] = gtime(); } } while (0)
 template <bool COUNT>
-__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(IterParams p) {
+__device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
     constexpr int kWarps = kNnThreads / 32;
     // per-thread running sums live in shared memory (s_acc[k][thread]) so that the search loop keeps its registers
     __shared__ double s_acc[kSums][kNnThreads];
@@ -463,8 +471,8 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
     __shared__ double s_norm;
     __shared__ int s_last;
     IcpState *st = p.st;
-    if (p.respect_done && st->done) return;
-    if (threadIdx.x == 0) s_est = st->est;
+    if (p.respect_done && __ldcg(&st->done)) return;
+    if (threadIdx.x == 0) s_est = load_pose_cg(&st->est);
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x] = gtime();
 #pragma unroll
     for (int k = 0; k < kSums; ++k) s_acc[k][threadIdx.x] = 0.0;
@@ -768,6 +776,25 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
 }
 
+template <bool COUNT>
+__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(IterParams p) {
+    nn_search_iteration<COUNT>(p);
+}
+
+// The whole Gauss-Newton loop of one registration in ONE cooperative launch: every block runs the iteration above, the grid
+// meets at a barrier (the last block has solved and updated IcpState by then), and the loop ends when `done` is set — no
+// launch gap, no host poll between iterations.  Used for the small scans of the pipeline level, where an iteration is ~20 us
+// of work and the gaps were as long as the work (profiles/r01g_streaming.md).  Launched with cudaLaunchCooperativeKernel, which
+// refuses a grid that is not co-resident, so the barrier cannot deadlock.
+__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_persistent_kernel(IterParams p, int max_iterations) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    for (int i = 0; i < max_iterations; ++i) {
+        nn_search_iteration<false>(p);
+        grid.sync();  // block barrier + grid barrier + fence: the new estimate and `done` are visible to every block
+        if (*reinterpret_cast<volatile int *>(&p.st->done)) break;
+    }
+}
+
 // Neighbourhood statistics for the algorithmic-bytes figure: per query, how many of the 27 voxels exist
 // and how many points they hold.  One thread per (query, voxel).
 __global__ void nn_stats_kernel(const TblEntry *tbl, uint32_t mask, const double4 *src, uint32_t n, double vs, IcpState *st) {
@@ -813,11 +840,10 @@ void VoxelMapGPU::profile_read(long long *launches, double *ms) {
     prof_used_ = 0;
 }
 
-// mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
-// as given; mode 2: as mode 1 with the search-work counters on.
-void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode,
-                                   double4 *tgt_out, uint8_t *matched_out) {
-    if (nn_grid_ == 0) {
+// one-time launch configuration of the search kernel (grid = co-resident blocks, tuning knobs from the environment)
+void VoxelMapGPU::init_search_config() {
+    if (nn_grid_ != 0) return;
+    {
         int per_sm = 0;
         SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_search_kernel<false>, kNnThreads, 0));
         nn_grid_ = sm_count_ * (per_sm > 0 ? per_sm : 1);
@@ -826,13 +852,30 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 3 / 4;
         if (const char *e = getenv("SAGE_ALL_WARP_MAX")) all_warp_max_ = (size_t)atol(e);
         if (getenv("SAGE_NO_ALL_WARP")) all_warp_max_ = 0;
+        int coop = 0;
+        SAGE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+        int per_sm_p = 0;
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, nn_search_persistent_kernel, kNnThreads, 0));
+        persistent_grid_ = sm_count_ * per_sm_p;
+        if (persistent_grid_ > nn_grid_) persistent_grid_ = nn_grid_;  // partials_ is sized for nn_grid_
+        if (persistent_grid_ < 1) coop = 0;
+        persistent_max_ = coop ? 20000 : 0;  // scans up to this many queries run their GN loop in one cooperative launch
+        if (const char *e = getenv("SAGE_PERSISTENT_MAX")) persistent_max_ = coop ? (size_t)atol(e) : 0;
     }
+}
+
+// mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
+// as given; mode 2: as mode 1 with the search-work counters on.
+void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode,
+                                   double4 *tgt_out, uint8_t *matched_out, int persistent_iters) {
+    init_search_config();
     // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
     // there is a chunk for every block, fewer blocks for small scans
     // small scans: one warp per query (all_warp) as long as that is at most two queries per resident warp
     const bool all_warp = n <= all_warp_max_;
     uint32_t grid = all_warp ? (uint32_t)((n + kNnThreads / 32 - 1) / (kNnThreads / 32)) : (uint32_t)((n + 31) / 32);
     grid = grid < 1 ? 1 : (grid > (uint32_t)nn_grid_ ? (uint32_t)nn_grid_ : grid);
+    if (persistent_iters > 0 && grid > (uint32_t)persistent_grid_) grid = (uint32_t)persistent_grid_;  // must be co-resident
 
     IterParams p;
     p.tbl = tbl_.p, p.mask = tbl_cap_ - 1, p.blk_pts = blk_pts_.p, p.blk_hot = blk_hot_.p, p.stride = stride_, p.voxel_size = voxel_size_;
@@ -878,10 +921,15 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         }
         SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].first, stream_));
     }
-    if (mode == 2)
+    if (persistent_iters > 0) {
+        void *args[] = {&p, &persistent_iters};
+        SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (mode == 2) {
         SAGE_LAUNCH(nn_search_kernel<true>, grid, kNnThreads, 0, stream_, p);
-    else
+    } else {
         SAGE_LAUNCH(nn_search_kernel<false>, grid, kNnThreads, 0, stream_, p);
+    }
     if (prof) {
         SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].second, stream_));
         ++prof_used_;
@@ -910,6 +958,14 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     // iterations are launched in batches (kernels of a finished registration return at once) and `done` is polled between
     // batches; the first batch is sized from the previous registration so that the common case needs one round trip
     int launched = 0;
+    // small scans, single rank: the whole loop in one cooperative launch (nn_search_persistent_kernel)
+    init_search_config();
+    if (n <= persistent_max_ && comm_ == nullptr && peer_world_ <= 1 && !dbg_on_) {
+        launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, max_iters);
+        SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
+        SAGE_CUDA(cudaStreamSynchronize(stream_));
+        launched = max_iters;
+    }
     while (launched < max_iters) {
         int batch = launched == 0 ? (last_iters_ + 2 > 8 ? last_iters_ + 2 : 8) : 8;
         if (batch > 48) batch = 48;

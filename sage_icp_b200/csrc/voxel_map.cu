@@ -415,7 +415,9 @@ void VoxelMapGPU::reserve(size_t extra) {
     if (need_blocks || need_tbl) sync_stats();  // tighten the bounds before paying for growth
     if (hi_bound_ + extra > blk_cap_) {
         size_t want = std::max<size_t>(hi_bound_ + extra, (size_t)blk_cap_ * 2);
-        want = std::max<size_t>(want, 4096);
+        // first allocation: room for 64 Ki voxels (126 MB with 40 slots per voxel) so that a streaming map does not pay a
+        // reallocate-and-copy step (cudaMalloc + cudaFree: ~10 ms, device-synchronising) every time it doubles early in a drive
+        want = std::max<size_t>(want, 65536);
         if (want > 0x7fffffffull / (size_t)stride_) throw ArgError("voxel map too large");
         blk_key_.ensure(want, stream_, true);
         blk_cnt_.ensure(want, stream_, true);

@@ -125,7 +125,8 @@ private:
     void reserve(size_t extra_points);  // make room for up to `extra_points` new voxels
     void rebuild_table(uint32_t new_cap);
     void launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
-                          uint8_t *matched_out);
+                          uint8_t *matched_out, int persistent_iters = 0);
+    void init_search_config();
     void set_device() const { SAGE_CUDA(cudaSetDevice(device_)); }
 
     double voxel_size_, max_distance_;
@@ -169,6 +170,8 @@ private:
     DevBuf<double> partials_;
     int nn_grid_ = 0;
     size_t all_warp_max_ = 0;  // scans up to this many queries use the warp-per-query mode
+    int persistent_grid_ = 0;    // co-resident blocks of the persistent kernel
+    size_t persistent_max_ = 0;  // scans up to this many queries run the whole GN loop in one cooperative launch
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
     int light_probes_ = -1;  // < 0: chosen from the number of queries (launch_iteration); SAGE_LIGHT_PROBES overrides
     bool dbg_on_ = false;

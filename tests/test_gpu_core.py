@@ -239,6 +239,35 @@ def test_register_frame_device_resident_matches_host_path(orc):
     assert torch.equal(d.cpu(), torch.from_numpy(scan))  # the caller's frame is not modified (the reference copies it)
 
 
+@pytest.mark.parametrize("n_az", [60, 300])
+def test_persistent_loop_equals_one_launch_per_iteration(orc, monkeypatch, n_az):
+    """Small scans run their whole Gauss-Newton loop in one cooperative launch (nn_search_persistent_kernel); the result is
+    bit-identical to one launch per iteration (SAGE_PERSISTENT_MAX=0 switches the former off), for the warp-per-query mode
+    (60 x 32 queries) and the thread-per-query mode (300 x 32), and both equal the oracle within tolerance."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    o = orc.OracleMap(0.8, 100.0, 20, 20, BASIC_LABELS, evict_faithful=False)
+    o.add_points(_street_points(300_000, 29))
+    scan = syn.make_scan(6, (0.0, 0.0, 0.0), n_beams=32, n_az=n_az)
+    guess = syn.pose7_from_xyyaw((0.25, -0.1, 0.01))
+    out = []
+    for persistent_max in ("0", "20000"):
+        monkeypatch.setenv("SAGE_PERSISTENT_MAX", persistent_max)  # read when the map's search is first configured
+        g = sg.SageMap(0.8, 100.0, 20, 20, BASIC_LABELS)
+        g.load(*o.dump())
+        before = sg.launch_count()
+        pose, it = g.register_frame(scan, guess, 3.0, 0.33, 0.4)
+        out.append((pose, it, sg.launch_count() - before))
+        pose_again, it_again = g.register_frame(scan, guess, 3.0, 0.33, 0.4)
+        assert it_again == it and np.array_equal(pose_again, pose)  # reproducible
+    (p0, it0, l0), (p1, it1, l1) = out
+    assert it0 == it1 and it0 > 2 and np.array_equal(p0, p1)
+    assert l1 < l0 and l1 <= 3  # init + one cooperative launch (+ nothing per iteration)
+    po, ito = o.register_frame_core(scan, guess, 3.0, 0.33, 0.4)
+    dt, da = pose_delta(p1, po)
+    assert ito == it1 and dt <= POSE_TOL_M and da <= POSE_TOL_RAD
+
+
 def test_nn_stats_match_oracle(orc):
     g, o = _maps(orc)
     o.add_points(_street_points(200_000, 9))

@@ -56,7 +56,8 @@ def main():
     print(json.dumps({
         "workload": "BASELINE configs[2]: streaming RegisterFrame, synthetic KITTI-shaped drive, incremental Update on device",
         "frames": a.frames, "dynamic_vehicle_filter": bool(a.dynamic_filter), "rays_per_scan": a.beams * a.az, "gpu_frames_per_s": float(1.0 / g.mean()), "gpu_ms_per_frame_median": float(1e3 * np.median(g)),
-        "gpu_ms_per_frame_p99": float(1e3 * np.percentile(g, 99)), "mean_gn_iterations": float(np.mean(iters)),
+        "gpu_ms_per_frame_p99": float(1e3 * np.percentile(g, 99)),
+        "slowest_frames (index, ms)": [(int(i) + warm, round(float(1e3 * g[i]), 3)) for i in np.argsort(g)[-5:][::-1]], "mean_gn_iterations": float(np.mean(iters)),
         "mean_t_icp_ms": float(1e3 * np.mean(t_icps[warm:])), "mean_t_all_ms (front end + icp, reference meaning)": float(1e3 * np.mean(t_alls[warm:])), "mean_queries": float(np.mean(nsrc)),
         "map_voxels_end": gp.map().num_voxels(), "map_points_end": gp.map().num_points(), "gpu_launches_per_frame": (sg.launch_count() - l0) / a.frames,
         "cpu_port_frames_per_s": float(1.0 / c.mean()), "cpu_cores": orc.max_threads(), "cpu_frames_timed": int(len(c)),

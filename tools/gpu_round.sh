@@ -12,3 +12,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 4
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:nn_search -s 40 -c 2 -f -o gpurun_out/prof_nn \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_full.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err; cat gpurun_out/bench_reference.json
+timeout 150 python tools/stream_bench.py --frames 300 --cpu-frames 40 > gpurun_out/stream_300.json 2> gpurun_out/stream_300.err; tail -c 900 gpurun_out/stream_300.json

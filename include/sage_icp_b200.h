@@ -67,6 +67,10 @@ sage_pipeline *sage_create(const sage_config_pod *config, int device);
 void sage_destroy(sage_pipeline *h);
 /* sageICP::reinitialize() — pipeline/sageICP.hpp:94-99 */
 int sage_reset(sage_pipeline *h);
+/* Move a fresh (or just reinitialised) pipeline to another GPU: ids[0] = CUDA ordinal, n must be 1 — a handle runs on one GPU;
+ * several GPUs are used as one process per GPU over the core-level sage_map_comm_* entry points below.
+ * The reference has no counterpart (CPU only); this is the device selection of its drop-in. */
+int sage_set_devices(sage_pipeline *h, const int *ids, int n);
 
 /* sageICP::RegisterFrame(frame[, timestamps]) — pipeline/sageICP.cpp:36-52 and :54-95.
  * xyzl: HOST pointer, n x 4 doubles.  timestamps: NULL or n doubles (used only when config.deskew).

@@ -303,6 +303,11 @@ class SagePipeline:
 
     def reinitialize(self): self._chk(self.L.sage_reset(self.h), "sage_reset")
 
+    def set_devices(self, ids):
+        """Move a fresh pipeline to GPU ids[0] (exactly one id: a handle runs on one GPU)."""
+        a = (C.c_int * len(ids))(*ids)
+        self._chk(self.L.sage_set_devices(self.h, a, len(ids)), "sage_set_devices")
+
     def register_frame(self, pts, timestamps=None):
         """RegisterFrame(frame[, timestamps]) -> (pose7, t_icp, t_all); `source` via last_source()."""
         pts = _c64(pts); pose = np.empty(7); ti, ta = C.c_double(), C.c_double()

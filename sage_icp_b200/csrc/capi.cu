@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/sage_icp_b200.h.  Exceptions never cross the boundary: they become
 // negative return codes + sage_last_error().
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "../../include/sage_icp_b200.h"
@@ -13,10 +14,38 @@ struct sage_map {
     VoxelMapGPU *impl;
     bool owned;
 };
+// deep copy of a sageConfig POD (the caller's arrays need not outlive sage_create)
+struct ConfigCopy {
+    sage_config_pod pod{};
+    std::vector<int32_t> offsets, labels, basic, landmarks;
+    std::vector<double> sizes;
+    explicit ConfigCopy(const sage_config_pod &c) : pod(c) {
+        if (c.n_groups < 0 || c.n_basic_parts_labels < 0 || c.n_dynamic_remove_lankmark < 0) throw ArgError("sageConfig: negative array length");
+        if (c.n_groups > 0 && (!c.group_offsets || !c.voxel_size)) throw ArgError("sageConfig: voxel_size / group_offsets is NULL");
+        if (c.n_groups > 0) offsets.assign(c.group_offsets, c.group_offsets + c.n_groups + 1), sizes.assign(c.voxel_size, c.voxel_size + c.n_groups);
+        const int n_labels = offsets.empty() ? 0 : offsets.back();
+        if (n_labels < 0 || (n_labels > 0 && !c.group_labels)) throw ArgError("sageConfig: group_labels is NULL or group_offsets negative");
+        if (n_labels > 0) labels.assign(c.group_labels, c.group_labels + n_labels);
+        if (c.n_basic_parts_labels > 0) {
+            if (!c.basic_parts_labels) throw ArgError("sageConfig: basic_parts_labels is NULL");
+            basic.assign(c.basic_parts_labels, c.basic_parts_labels + c.n_basic_parts_labels);
+        }
+        if (c.n_dynamic_remove_lankmark > 0) {
+            if (!c.dynamic_remove_lankmark) throw ArgError("sageConfig: dynamic_remove_lankmark is NULL");
+            landmarks.assign(c.dynamic_remove_lankmark, c.dynamic_remove_lankmark + c.n_dynamic_remove_lankmark);
+        }
+        pod.group_offsets = offsets.data(), pod.group_labels = labels.data(), pod.voxel_size = sizes.data();
+        pod.basic_parts_labels = basic.data(), pod.dynamic_remove_lankmark = landmarks.data();
+    }
+    ConfigCopy(const ConfigCopy &) = delete;
+    ConfigCopy &operator=(const ConfigCopy &) = delete;
+};
 struct sage_pipeline {
     Pipeline *impl;
     sage_map map_handle;
     std::vector<double> scratch;
+    ConfigCopy *config;
+    int device;
 };
 
 static thread_local std::string g_err;
@@ -85,8 +114,10 @@ sage_pipeline *sage_create(const sage_config_pod *config, int device) {
     sage_pipeline *h = nullptr;
     const long long rc = guarded([&] {
         if (!config) throw ArgError("config is NULL");
-        auto *p = new Pipeline(*config, device);
-        h = new sage_pipeline{p, sage_map{&p->map(), false}, {}};
+        std::unique_ptr<ConfigCopy> copy(new ConfigCopy(*config));
+        std::unique_ptr<Pipeline> p(new Pipeline(copy->pod, device));
+        h = new sage_pipeline{p.get(), sage_map{&p->map(), false}, {}, copy.get(), device};
+        p.release(), copy.release();
         return 0;
     });
     return rc == 0 ? h : nullptr;
@@ -94,7 +125,27 @@ sage_pipeline *sage_create(const sage_config_pod *config, int device) {
 void sage_destroy(sage_pipeline *h) {
     if (!h) return;
     delete h->impl;
+    delete h->config;
     delete h;
+}
+int sage_set_devices(sage_pipeline *h, const int *ids, int n) {
+    return (int)guarded([&] {
+        P(h);
+        need(ids, "ids");
+        if (n != 1)
+            throw ArgError("a handle runs on one GPU: use one process per GPU and sage_map_comm_peer_attach / sage_map_comm_init to shard a "
+                           "registration over several");
+        if (ids[0] == h->device) return 0;
+        if (!h->impl->poses().empty() || !h->impl->map().empty()) throw ArgError("the device can only be changed on a fresh or reinitialised pipeline");
+        std::unique_ptr<Pipeline> p(new Pipeline(h->config->pod, ids[0]));  // throws if the device is unusable; the old one stays
+        const bool faithful = h->impl->map().eviction_faithful();
+        p->map().set_eviction_faithful(faithful);
+        delete h->impl;
+        h->impl = p.release();
+        h->map_handle = sage_map{&h->impl->map(), false};
+        h->device = ids[0];
+        return 0;
+    });
 }
 int sage_reset(sage_pipeline *h) {
     return (int)guarded([&] {

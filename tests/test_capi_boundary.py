@@ -219,7 +219,7 @@ def test_null_handles_are_error_codes_not_crashes(lib):
     d7 = (C.c_double * 7)()
     null = C.c_void_p(None)
     for name, args in [("sage_reset", ()), ("sage_last_iterations", ()), ("sage_has_moved", ()), ("sage_get_prediction_model", (d7,)),
-                       ("sage_get_pose", (C.c_size_t(0), d7)), ("sage_register_frame", (None, C.c_size_t(0), None, d7, None, None))]:
+                       ("sage_get_pose", (C.c_size_t(0), d7)), ("sage_set_devices", ((C.c_int * 1)(0), 1)), ("sage_register_frame", (None, C.c_size_t(0), None, d7, None, None))]:
         rc = getattr(L, name)(null, *args)
         assert rc < 0, name
         assert b"null" in L.sage_last_error(), name

@@ -98,6 +98,26 @@ def test_reinitialize(orc, cfg):
     assert np.allclose(pose, [0, 0, 0, 0, 0, 0, 1])
 
 
+def test_set_devices(orc, cfg):
+    """sage_set_devices: one id per handle; a no-op for the current device; refused once the pipeline holds state; moving a
+    fresh pipeline to another GPU (when the box has one) gives the same poses."""
+    import sage_icp_b200 as sg
+    gp = sg.SagePipeline(cfg)
+    gp.set_devices([0])
+    with pytest.raises(sg.SageError, match="one GPU"):
+        gp.set_devices([0, 1])
+    with pytest.raises(sg.SageError):
+        gp.set_devices([sg.device_count()])  # no such device; the handle keeps working on the old one
+    ref = [gp.register_frame(_scan(i, (0.2 * i, 0, 0)))[0] for i in range(3)]
+    with pytest.raises(sg.SageError, match="fresh"):
+        gp.set_devices([1])
+    if sg.device_count() >= 2:
+        other = sg.SagePipeline(cfg)
+        other.set_devices([1])
+        for i in range(3):
+            assert np.array_equal(other.register_frame(_scan(i, (0.2 * i, 0, 0)))[0], ref[i])
+
+
 def test_bad_config_fails_loudly(cfg):
     import sage_icp_b200 as sg
     from sage_icp_b200.config import SageConfig, launch_config

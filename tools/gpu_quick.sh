@@ -1,4 +1,4 @@
 #!/bin/bash
-# scratch: validate the boundary changes (config deep copy, sage_set_devices) on the pipeline path
+# scratch: 2-GPU lock-step tests after the kernel-body refactor
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_pipeline.py tests/test_cpp_adaptor.py tests/test_capi_boundary.py -x -q --timeout 120 --timeout-method=thread 2>&1 | tail -6 | tee gpurun_out/quick_boundary.log
+timeout 150 python -m pytest tests/test_gpu_multirank.py -x -q -m gpu --timeout 100 --timeout-method=thread 2>&1 | tail -6 | tee gpurun_out/quick_multirank.log

@@ -38,14 +38,18 @@ void robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out
     auto make = [](int d, uint64_t rest) { return ((uint64_t)d << 48) | rest; };  // rest = hash << 28 | val
 
     // robin-hood swap-and-carry of `rest` from bucket ib with distance d
+    // (tsl marks the table for growth when a CARRIED element is swapped in at a distance >= the limit; the new element's own
+    // first swap is not checked)
     auto place = [&](uint64_t *T, size_t msk, size_t ib, int d, uint64_t rest, bool track) {
+        bool carried = false;
         while (true) {
             const uint64_t e = T[ib];
             const int ed = dist_of(e);
             if (d > ed) {
                 T[ib] = make(d, rest);
                 if (ed < 0) return;
-                if (track && d >= kDistLimit) grow_next = true;
+                if (track && carried && d >= kDistLimit) grow_next = true;
+                carried = true;
                 d = ed, rest = e & 0xffffffffffffull;
             }
             ++d;

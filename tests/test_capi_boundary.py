@@ -235,3 +235,34 @@ def test_null_handles_are_error_codes_not_crashes(lib):
     L.sage_map_stream.restype = C.c_void_p
     assert L.sage_pipeline_map(null) is None and L.sage_map_stream(null) is None
     L.sage_destroy(null); L.sage_map_destroy(null)  # no-ops
+
+
+def test_product_robin_replay_at_the_probe_length_limit(lib, orc):
+    """The down-sampler's replay (csrc/frontend.cu) where the probe-length limit (8192) forces a growth: 8300 keys whose hashes
+    agree in the low 15 bits; same order as the oracle's RobinTable."""
+    import sage_icp_b200 as sg
+    keys = _colliding_keys(8300, [77 + (j << 15) for j in range(32)], 6)
+    h = np.array([orc.voxel_hash(*[int(v) for v in k]) for k in keys], dtype=np.uint32)
+    got = sg.robin_iteration_order(h)
+    want, buckets = orc.robin_order(keys)
+    assert buckets == 1 << 16
+    assert np.array_equal(got.astype(np.int64), want)
+
+
+def test_robin_tables_agree_when_the_new_element_itself_lands_at_the_limit(lib, orc):
+    """Corner of the growth rule: the inserted element's first swap happens at distance exactly 8192 (a second cluster sits right
+    behind an 8192-long run).  tsl only marks the table for growth when a CARRIED element is swapped at >= 8192, so no extra
+    growth here — the oracle's table, the down-sampler's replay and the map's host mirror must all agree."""
+    import sage_icp_b200 as sg
+    c = 77
+    run = _colliding_keys(8300, [c + (j << 15) for j in range(32)], 7)        # ideal bucket c while the table has 2^15 buckets
+    behind = _colliding_keys(40, [c + 8192 + (j << 15) for j in range(32)], 8)  # ideal bucket c + 8192: right behind the run
+    after = _colliding_keys(10, [5], 9)  # inserted after the corner case: a table wrongly marked for growth would double now
+    keys = np.concatenate([run[:4000], behind, run[4000:8193], after])
+    assert len(np.unique(keys, axis=0)) == len(keys)
+    h = np.array([orc.voxel_hash(*[int(v) for v in k]) for k in keys], dtype=np.uint32)
+    want, buckets = orc.robin_order(keys)
+    got = sg.robin_iteration_order(h)
+    assert np.array_equal(got.astype(np.int64), want)
+    got2, buckets2 = sg.robin_table_replay(np.c_[np.zeros(len(keys), np.int32), keys, np.zeros(len(keys), np.int32)])
+    assert buckets2 == buckets == 1 << 15 and np.array_equal(got2, keys[want])

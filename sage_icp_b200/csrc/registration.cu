@@ -459,7 +459,7 @@ __device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s
 // Queries are dealt to warps in chunks of 32 consecutive points, chunk c to block c % grid, so every block sees a
 // cross-section of the scan and the expensive regions (sparse, far from the sensor) spread over all SMs.
 #define SAGE_STAMP(i) do { if (p.dbg && pass == 0 && warp == 0) { __syncwarp(); if (lane == 0) p.dbg[kDbg * blockIdx.x + (i)] = gtime(); } } while (0)
-template <bool COUNT>
+template <bool COUNT, bool POOLED = false>
 __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
     constexpr int kWarps = kNnThreads / 32;
     // per-thread running sums live in shared memory (s_acc[k][thread]) so that the search loop keeps its registers
@@ -551,6 +551,108 @@ __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
             if (COUNT) n_scanned += hcnt;
         }
         SAGE_STAMP(6);
+        if constexpr (POOLED) {
+            // EXPERIMENTAL (SAGE_POOLED=1; written at the end of round 1 from the schedule model in profiles/r01l_visit_schedule_model.md,
+            // not yet run on a GPU).  Neighbour visits of the warp's 32 queries are pooled: every round each still-open query
+            // nominates its nearest open boxes, floor(32 / open queries) of them, the 32 lanes take one (query, voxel) visit each,
+            // and every query merges the (min1, min2, arg) results of its own visits; bounds are re-tightened between rounds.
+            // A warp pays sum-of-visits / 32 rounds instead of the visits of its slowest lane, and nothing is deferred.
+            __shared__ uint16_t s_item[kWarps][32];
+            __shared__ float s_r1[kWarps][32], s_r2[kWarps][32];
+            __shared__ uint32_t s_ri[kWarps][32];
+            const unsigned FULL = 0xffffffffu;
+            float sxm = 0, sxp = 0, sym = 0, syp = 0, szm = 0, szp = 0;
+            bool open_query = valid && !odd;
+            if (open_query) {
+                if (COUNT) n_probes += 1;
+                axis_bounds(bx, kx, vs32, p.box_margin, p.smin32, sxm, sxp);
+                axis_bounds(by, ky, vs32, p.box_margin, p.smin32, sym, syp);
+                axis_bounds(bz, kz, vs32, p.box_margin, p.smin32, szm, szp);
+            }
+            auto box_lb = [&](int id) {
+                const int ox = id / 9, oy = (id / 3) % 3, oz = id % 3;
+                return (ox == 0 ? sxm : (ox == 2 ? sxp : 0.0f)) + (oy == 0 ? sym : (oy == 2 ? syp : 0.0f)) + (oz == 0 ? szm : (oz == 2 ? szp : 0.0f));
+            };
+            uint32_t visited = 1u << 13;
+#pragma unroll 1
+            while (true) {
+                uint32_t open = 0;
+                if (open_query && !odd) {
+                    const float bound = prune_bound(p, min1);
+#pragma unroll 1
+                    for (int id = 0; id < 27; ++id)
+                        if (!((visited >> id) & 1u) && box_lb(id) <= bound) open |= 1u << id;
+                }
+                const unsigned am = __ballot_sync(FULL, open != 0);
+                if (am == 0) break;
+                const int quota = max(1, 32 / __popc(am));
+                const int mine = min(quota, __popc(open));
+                int pre = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(FULL, pre, o);
+                    if (lane >= o) pre += t;
+                }
+                const int start = pre - mine, total = __shfl_sync(FULL, pre, 31);  // total <= open queries * quota <= 32
+                uint32_t left = open;
+#pragma unroll 1
+                for (int t = 0; t < mine; ++t) {  // nearest open box first
+                    float best_lb = INF;
+                    int nn = -1;
+                    for (uint32_t m = left; m; m &= m - 1) {
+                        const int id = __ffs(m) - 1;
+                        const float lb = box_lb(id);
+                        if (lb < best_lb) best_lb = lb, nn = id;
+                    }
+                    left &= ~(1u << nn);
+                    visited |= 1u << nn;
+                    s_item[warp][start + t] = (uint16_t)((lane << 8) | nn);
+                }
+                __syncwarp();
+                // lane j takes visit j: the owner's query through shuffles, the voxel from the item
+                const bool have = lane < total;
+                const uint32_t item = have ? s_item[warp][lane] : (uint32_t)(lane << 8);
+                const int ql = (int)(item >> 8), id = (int)(item & 0xffu);
+                const int qkx = __shfl_sync(FULL, kx, ql), qky = __shfl_sync(FULL, ky, ql), qkz = __shfl_sync(FULL, kz, ql);
+                const float qbx = __shfl_sync(FULL, bx, ql), qby = __shfl_sync(FULL, by, ql), qbz = __shfl_sync(FULL, bz, ql);
+                const float qql = __shfl_sync(FULL, qlf, ql);
+                float r1 = INF, r2 = INF;
+                uint32_t ri = kNil;
+                bool rodd = false;
+                if (have) {
+                    const int ox = id / 9 - 1, oy = (id / 3) % 3 - 1, oz = id % 3 - 1;
+                    const int nx = qkx + ox, ny = qky + oy, nz = qkz + oz;
+                    uint32_t nblk = 0, ncnt = 0;
+                    if (COUNT) n_probes += 1;
+                    if (key_in_range(nx, ny, nz) && tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), nblk, ncnt) && ncnt > 0) {
+                        scan_voxel_thread(p.blk_hot, nblk * (uint32_t)p.stride, ncnt, qbx - (float)ox * vs32, qby - (float)oy * vs32,
+                                          qbz - (float)oz * vs32, qql, th32, r1, r2, ri, rodd);
+                        if (COUNT) n_scanned += ncnt;
+                    }
+                }
+                s_r1[warp][lane] = r1, s_r2[warp][lane] = r2, s_ri[warp][lane] = ri;
+                const unsigned oddm = __ballot_sync(FULL, rodd);
+                __syncwarp();
+#pragma unroll 1
+                for (int t = 0; t < mine; ++t) {  // merge: (min1, min2, arg) of the union of two record sets; a tie keeps min2 == min1
+                    const int j = start + t;
+                    const float a1 = s_r1[warp][j], a2 = s_r2[warp][j];
+                    if (a1 < min1) {
+                        min2 = fminf(min1, a2), min1 = a1, idx1 = s_ri[warp][j];
+                    } else {
+                        min2 = fminf(min2, a1);
+                    }
+                    odd |= ((oddm >> j) & 1u) != 0;
+                }
+                __syncwarp();  // s_item / s_r* are rewritten by the next round
+            }
+            if (open_query && !odd && min1 < INF) {
+                if (min2 > band_limit(p, min1))
+                    widx = idx1;
+                else
+                    odd = true;
+            }
+        } else
         if (valid && !odd) {
             if (COUNT) n_probes += 1;
             // ---- neighbours, nearest bounding box first, while one can still beat the best so far ----
@@ -780,6 +882,11 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(IterParams p) {
     nn_search_iteration<COUNT>(p);
 }
+// EXPERIMENTAL, off unless SAGE_POOLED=1: the pooled neighbour schedule (see nn_search_iteration)
+template <bool COUNT>
+__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_pooled_kernel(IterParams p) {
+    nn_search_iteration<COUNT, true>(p);
+}
 
 // The whole Gauss-Newton loop of one registration in ONE cooperative launch: every block runs the iteration above, the grid
 // meets at a barrier (the last block has solved and updated IcpState by then), and the loop ends when `done` is set — no
@@ -852,6 +959,7 @@ void VoxelMapGPU::init_search_config() {
         all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 3 / 4;
         if (const char *e = getenv("SAGE_ALL_WARP_MAX")) all_warp_max_ = (size_t)atol(e);
         if (getenv("SAGE_NO_ALL_WARP")) all_warp_max_ = 0;
+        if (const char *e = getenv("SAGE_POOLED")) pooled_ = atoi(e) != 0;  // experimental schedule, see nn_search_iteration
         int coop = 0;
         SAGE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
         int per_sm_p = 0;
@@ -925,6 +1033,11 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         void *args[] = {&p, &persistent_iters};
         SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else if (pooled_) {
+        if (mode == 2)
+            SAGE_LAUNCH(nn_search_pooled_kernel<true>, grid, kNnThreads, 0, stream_, p);
+        else
+            SAGE_LAUNCH(nn_search_pooled_kernel<false>, grid, kNnThreads, 0, stream_, p);
     } else if (mode == 2) {
         SAGE_LAUNCH(nn_search_kernel<true>, grid, kNnThreads, 0, stream_, p);
     } else {

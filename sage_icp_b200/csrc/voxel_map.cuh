@@ -170,6 +170,7 @@ private:
     DevBuf<double> partials_;
     int nn_grid_ = 0;
     size_t all_warp_max_ = 0;  // scans up to this many queries use the warp-per-query mode
+    bool pooled_ = false;        // SAGE_POOLED=1: experimental pooled neighbour schedule of the search kernel
     int persistent_grid_ = 0;    // co-resident blocks of the persistent kernel
     size_t persistent_max_ = 0;  // scans up to this many queries run the whole GN loop in one cooperative launch
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)

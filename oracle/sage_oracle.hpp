@@ -2,10 +2,13 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may use it.
 //
 // CPU restatement (f64, structurally faithful: per-voxel std::vector storage, per-query candidate copy,
-// sequential map insert) of the SAGE-ICP per-scan registration hot path. The reference itself cannot be
-// compiled here (Eigen, Sophus, oneTBB, tsl::robin_map, PCL absent) so this file IS the
-// checker. PARITY UNPINNED: the reference ships no tests or golden vectors; the oracle is
-// cross-checked by independent numpy/scipy restatements in tests/.
+// sequential map insert) of the SAGE-ICP per-scan registration hot path. The reference cannot be built as it
+// stands (Eigen, Sophus, oneTBB, tsl::robin_map, PCL absent) and ships no tests or golden
+// vectors, so this file is the checker.  It is itself checked (a) against the reference's own
+// hot-path sources compiled here against stand-in third-party headers (oracle/shim/, oracle/_ref,
+// tests/test_reference_build.py: bit-identical on the integer/index work, poses to rounding) and (b) against
+// independent numpy/scipy restatements (tests/test_oracle_*.py).  Parity with the real third-party binaries
+// (LDLT / exp / log rounding, tsl bucket order, PCL cluster order) remains UNPINNED.
 //
 // Deliberate deviations (documented in DESIGN.md):
 //   * empty 27-neighbourhood => "no correspondence" (the reference reads an uninitialised vector,

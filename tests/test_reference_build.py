@@ -239,3 +239,37 @@ def test_transform_to_last_frame(ref, orc, cfg):
     T = orc.se3_mul(orc.se3_inverse(last), cur)
     exp = np.array([orc.se3_act(T, p[:3]) for p in pts])
     assert np.allclose(out[:, :3], exp, atol=1e-12) and np.array_equal(out[:, 3], pts[:, 3])
+
+
+def test_committed_golden_vectors_are_what_the_reference_build_computes(ref, cfg):
+    """tests/golden/*.npz were generated from the oracle; the GPU tests check the CUDA path against them on the GPU box.  Here
+    the reference's own code reproduces them: front end bit for bit, map contents bit for bit, matched targets bit for bit,
+    poses to rounding — so the fixtures are reference outputs in all but provenance."""
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    scan_of = lambda xyz, label: np.c_[xyz.astype(np.float64), label.astype(np.float64)]
+    g = np.load(os.path.join(G, "frontend.npz"))
+    cropped = ref.preprocess(cfg, scan_of(g["xyz"], g["label"]))
+    assert np.array_equal(cropped, g["cropped"])
+    ds = ref.voxel_downsample(cfg, cropped, 0.5)
+    assert np.array_equal(ds, g["downsample"]) and np.array_equal(ref.voxel_downsample(cfg, ds, 1.5), g["source"])
+
+    g = np.load(os.path.join(G, "core.npz"))
+    m = ref.RefMap(0.8, 100.0, 20, 20, BASIC_LABELS)
+    m.add_points(scan_of(g["map_xyz"], g["map_label"]))
+    keys, counts, vox = m.dump()
+    order = np.lexsort(keys.T[::-1])
+    assert np.array_equal(keys[order], g["keys"]) and np.array_equal(counts[order], g["counts"])
+    assert np.array_equal(vox[order], g["voxels"].astype(np.float64))
+    src, tgt = m.get_correspondences(g["queries"], 1.5, 0.4)
+    assert np.array_equal(src, g["queries"][g["matched_idx"]]) and np.array_equal(tgt, g["targets"])
+    pose = m.register_frame_core(g["queries"], g["guess"], 3.0, 1.0 / 3.0, 0.4)
+    assert np.allclose(pose, g["pose"], atol=1e-10)
+
+    g = np.load(os.path.join(G, "sequence.npz"))
+    p = ref.RefPipeline(cfg)
+    for i in range(len(g["xyz"])):
+        pose = p.register_frame(scan_of(g["xyz"][i], g["label"][i]))
+        assert np.allclose(pose, g["poses"][i], atol=1e-9), i
+        assert len(p.last_source()) == g["n_source"][i]
+    assert len(p.local_map()) == int(g["map_points"])

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Regenerates tests/golden/*.npz from the ORACLE (oracle/, the CPU restatement of the reference; the reference itself
-cannot be built or imported here — no Eigen/Sophus/TBB/tsl/PCL).  The fixtures pin (a) the oracle against
+"""Regenerates tests/golden/*.npz from the ORACLE (oracle/, the CPU restatement of the reference).  The reference's own sources,
+built against stand-in third-party headers (oracle/_ref), reproduce these files: tests/test_reference_build.py.  The fixtures pin (a) the oracle against
 silent regressions and (b) the CUDA path on the GPU box, where /root/reference and this generator's inputs need not exist.
 Run:  python tools/make_golden.py        (deterministic; commit the result)"""
 import os

@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -21,7 +22,12 @@ def test_reference_arm_prints_one_json_line():
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "scans/s" and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"]
+    # the value is the faster of the oracle port and the reference's own code (oracle/_ref), and the line says which
+    both = [v for v in (cb["port_value"], cb["reference_build_value"]) if v is not None]
+    assert d["value"] == pytest.approx(max(both))
+    assert (cb["kind"] == "reference") == (cb["reference_build_value"] is not None and cb["reference_build_value"] >= cb["port_value"])
     assert d["e2e"] == {"value": d["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

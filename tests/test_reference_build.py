@@ -273,3 +273,31 @@ def test_committed_golden_vectors_are_what_the_reference_build_computes(ref, cfg
         assert np.allclose(pose, g["poses"][i], atol=1e-9), i
         assert len(p.last_source()) == g["n_source"][i]
     assert len(p.local_map()) == int(g["map_points"])
+
+
+def test_long_drive_with_eviction(ref, orc):
+    """90 full-size scans (64 x 1875 rays, which the ICP tracks), 1 m per frame, 40 m map horizon: the map turns over, so the erase-while-iterating sweep, the
+    re-use of the robin_map's buckets and the adaptive threshold's accumulated state all matter.  Poses stay equal to rounding
+    for the whole drive and the final local map is the same, in order."""
+    from sage_icp_b200 import synthetic as syn
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config(local_map_range=40.0)
+    rp, op = ref.RefPipeline(cfg), orc.OraclePipeline(cfg, threads=orc.max_threads(), evict_faithful=True)
+    n = 90
+    traj = syn.trajectory(n)
+    worst = 0.0
+    for i in range(n):
+        scan = syn.make_scan(1000 + i, tuple(traj[i]), n_beams=64, n_az=1875)
+        pr = rp.register_frame(scan)
+        po, _, _ = op.register_frame(scan)
+        dt, da = pose_delta(pr, po)
+        worst = max(worst, dt)
+        assert dt < 1e-7 and da < 1e-8, (i, dt, da)
+        if i % 15 == 0:
+            assert np.array_equal(rp.last_source(), op.last_source()), i
+    a, b = rp.local_map(), op.local_map()
+    assert a.shape == b.shape
+    far = np.linalg.norm(a[:, :3] - rp.poses()[-1][:3], axis=1) > 40.0 + 2.0
+    assert rp.poses()[-1][0] - rp.poses()[0][0] > 60.0 and far.mean() < 0.2  # the vehicle out-drove the horizon: most old voxels are gone
+    assert np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a, b, atol=1e-6, rtol=0)
+    assert rp.adaptive_threshold() == pytest.approx(op.adaptive_threshold(), rel=1e-6)

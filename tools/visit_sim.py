@@ -92,6 +92,7 @@ def main():
             min1[r] = np.minimum(min1[r], best[r, j[r]])
             nv[r] += 1; nu[r] += nonempty[r, j[r]]
         visits[c0:c0 + m] = nv; useful[c0:c0 + m] = nu
+        assert np.array_equal(min1, best.min(1))  # pruned search == scan of all 27 voxels
         # per warp of 32 consecutive queries
         for w0 in range(0, m - m % 32, 32):
             sl = slice(w0, w0 + 32)
@@ -114,6 +115,7 @@ def main():
                     v2[r, idx] = True
                     m1[r] = min(m1[r], b2[r, idx].min())
             pooled_rounds.append(rounds)
+            assert np.array_equal(m1, b2.min(1))  # so does the pooled schedule
         print(f"  {min(c0 + a.chunk, n)} queries", end="\r", flush=True)
     warp_max, warp_sum, pooled_rounds = map(np.array, (warp_max, warp_sum, pooled_rounds))
     print()

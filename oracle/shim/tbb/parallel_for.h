@@ -1,9 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  NOT oneTBB.  tbb::parallel_for(first, last, f) over SAGE_REF_THREADS contiguous chunks
-// (default 1: a plain loop on the calling thread); see parallel_reduce.h.
+// (default 1: a plain loop on the calling thread) on the worker pool of parallel_reduce.h.
 #pragma once
-#include <thread>
-#include <vector>
-
 #include "parallel_reduce.h"
 
 namespace tbb {
@@ -15,12 +12,9 @@ void parallel_for(Index first, Index last, const F &f) {
         for (Index i = first; i < last; ++i) f(i);
         return;
     }
-    std::vector<std::thread> workers;
-    for (int t = 0; t < T; ++t)
-        workers.emplace_back([&, t] {
-            const Index b = first + (Index)((n * (std::size_t)t) / T), e = first + (Index)((n * (std::size_t)(t + 1)) / T);
-            for (Index i = b; i < e; ++i) f(i);
-        });
-    for (auto &w : workers) w.join();
+    shim_pool::instance().run(T, [&](int t) {
+        const Index b = first + (Index)((n * (std::size_t)t) / T), e = first + (Index)((n * (std::size_t)(t + 1)) / T);
+        for (Index i = b; i < e; ++i) f(i);
+    });
 }
 }  // namespace tbb

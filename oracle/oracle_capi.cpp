@@ -117,11 +117,14 @@ size_t orc_preprocess(const double *xyzl, size_t n, double max_range, double min
                       double *out, size_t cap) {
     return from_cloud(Preprocess(to_cloud(xyzl, n), max_range, min_range, label_max_range), out, cap);
 }
-size_t orc_preprocess_dynamic(const orc_config_pod *cfg, const double *xyzl, size_t n, double *out, size_t cap) {
+size_t orc_preprocess_dynamic_ordered(const orc_config_pod *cfg, const double *xyzl, size_t n, int cluster_order, double *out, size_t cap) {
     const Config c = to_config(cfg);
     return from_cloud(PreprocessDynamic(to_cloud(xyzl, n), c.max_range, c.min_range, c.label_max_range, c.dynamic_vehicle_filter_th,
-                                        c.voxel_labels[(size_t)c.dynamic_vehicle_voxid], c.dynamic_remove_lankmark),
+                                        c.voxel_labels[(size_t)c.dynamic_vehicle_voxid], c.dynamic_remove_lankmark, cluster_order != 0),
                       out, cap);
+}
+size_t orc_preprocess_dynamic(const orc_config_pod *cfg, const double *xyzl, size_t n, double *out, size_t cap) {
+    return orc_preprocess_dynamic_ordered(cfg, xyzl, n, 0, out, cap);
 }
 size_t orc_voxel_downsample(const orc_config_pod *cfg, const double *xyzl, size_t n, double vox_scale, double *out, size_t cap) {
     const Config c = to_config(cfg);
@@ -231,6 +234,7 @@ void *orc_create(const orc_config_pod *cfg, int threads, int evict_faithful) {
 }
 void orc_destroy(void *h) { delete (OrcPipeline *)h; }
 void orc_reset(void *h) { ((OrcPipeline *)h)->icp.reinitialize(); }
+void orc_set_dynamic_cluster_order(void *h, int on) { ((OrcPipeline *)h)->icp.dynamic_cluster_order_ = on != 0; }
 int orc_register_frame(void *h, const double *xyzl, size_t n, const double *ts, double pose_out[7], double *t_icp, double *t_all) {
     auto *p = (OrcPipeline *)h;
     const Cloud frame = to_cloud(xyzl, n);

@@ -38,7 +38,7 @@ def lib() -> C.CDLL:
         L.orc_create.restype = C.c_void_p
         L.orc_map_create.restype = C.c_void_p
         L.orc_pipeline_map.restype = C.c_void_p
-        for f in ("orc_preprocess", "orc_preprocess_dynamic", "orc_voxel_downsample", "orc_map_num_voxels", "orc_map_bucket_count", "orc_map_num_points",
+        for f in ("orc_preprocess", "orc_preprocess_dynamic", "orc_preprocess_dynamic_ordered", "orc_voxel_downsample", "orc_map_num_voxels", "orc_map_bucket_count", "orc_map_num_points",
                   "orc_map_pointcloud", "orc_map_dump", "orc_map_get_correspondences", "orc_last_source",
                   "orc_last_frame_downsample", "orc_num_poses", "orc_local_map", "orc_robin_order", "orc_voxelize", "orc_deskew"):
             getattr(L, f).restype = C.c_size_t
@@ -112,10 +112,11 @@ def preprocess(pts, max_range, min_range, label_max_range) -> np.ndarray:
     return out[:n].copy()
 
 
-def preprocess_dynamic(cfg, pts) -> np.ndarray:
-    """Preprocess with the dynamic-vehicle filter on (core/Preprocessing.cpp:95-172)."""
+def preprocess_dynamic(cfg, pts, cluster_order: bool = False) -> np.ndarray:
+    """Preprocess with the dynamic-vehicle filter on (core/Preprocessing.cpp:95-172).  cluster_order: re-admitted vehicle points
+    cluster by cluster in PCL's published order (as the reference emits them) instead of input order (what the CUDA path does)."""
     pod = cfg.to_pod(); pts = _c64(pts); out = np.empty_like(pts)
-    n = lib().orc_preprocess_dynamic(C.byref(pod), _d(pts), C.c_size_t(len(pts)), _d(out), C.c_size_t(len(pts)))
+    n = lib().orc_preprocess_dynamic_ordered(C.byref(pod), _d(pts), C.c_size_t(len(pts)), int(cluster_order), _d(out), C.c_size_t(len(pts)))
     return out[:n].copy()
 
 
@@ -214,6 +215,10 @@ class OraclePipeline:
             lib().orc_destroy(self.h); self.h = None
 
     def reset(self): lib().orc_reset(self.h)
+
+    def set_dynamic_cluster_order(self, on: bool):
+        """Dynamic-vehicle filter: emit the re-admitted vehicle points cluster by cluster (the reference's order) instead of input order."""
+        lib().orc_set_dynamic_cluster_order(self.h, int(bool(on)))
 
     def register_frame(self, pts, timestamps: Optional[np.ndarray] = None):
         pts = _c64(pts); pose = np.empty(7); ti, ta = C.c_double(), C.c_double()

@@ -84,11 +84,14 @@ inline Cloud Preprocess(const Cloud &frame, double max_range, double min_range, 
 // published behaviour: a cluster is a connected component of the graph "squared f32 distance < 0.5^2" (FLANN's radius
 // result set keeps dist < radius); a cluster is kept (static vehicle) iff the landmark hits summed over its points exceed
 // int(dy_th * size) — the reference's early `break` only short-circuits that monotone count.
-// PARITY UNPINNED, and one documented difference: the kept clusters' points are appended in INPUT order, whereas PCL emits
-// clusters by descending size (std::sort, ties unspecified) and points in breadth-first order of its kd-tree queries.  The
-// retained point SET is the reference's; the order of the appended vehicle points is this restatement's.
+// The retained point SET is pinned against the reference's own filter code run over a stand-in for PCL
+// (tests/test_reference_build.py); parity with PCL itself is UNPINNED.  Order of the re-admitted vehicle points:
+//   cluster_order = false (default; what the CUDA path does): input order;
+//   cluster_order = true: cluster by cluster as the reference emits them, with PCL's published ordering — clusters by
+//     descending size (equal sizes: discovery order here, unspecified in PCL's unstable std::sort), indices inside a cluster
+//     ascending — which reproduces the reference build's output in order.
 inline Cloud PreprocessDynamic(const Cloud &frame, double max_range, double min_range, double label_max_range, double dy_th,
-                               const std::vector<int> &dynamic_labels, const std::vector<int> &lankmark) {
+                               const std::vector<int> &dynamic_labels, const std::vector<int> &lankmark, bool cluster_order = false) {
     struct P {
         float x, y, z;
         uint32_t label;
@@ -128,17 +131,29 @@ inline Cloud PreprocessDynamic(const Cloud &frame, double max_range, double min_
         clusters.push_back(std::move(members));
     }
     std::vector<char> keep(nv, 0);
+    std::vector<const std::vector<size_t> *> kept;
     for (const auto &members : clusters) {
         if (members.size() < 5) continue;  // setMinClusterSize(5)
         long long count = 0;
         for (size_t i : members)
             for (const auto &q : all)
                 if (std::find(lankmark.begin(), lankmark.end(), (int)q.label) != lankmark.end() && near(veh[i], q)) ++count;
-        if (count > (long long)(int)(dy_th * (double)members.size()))
+        if (count > (long long)(int)(dy_th * (double)members.size())) {
             for (size_t i : members) keep[i] = 1;
+            kept.push_back(&members);
+        }
     }
-    for (size_t i = 0; i < nv; ++i)
-        if (keep[i]) inliers.push_back(vehicle_inliers[i]);
+    if (!cluster_order) {
+        for (size_t i = 0; i < nv; ++i)
+            if (keep[i]) inliers.push_back(vehicle_inliers[i]);
+        return inliers;
+    }
+    std::stable_sort(kept.begin(), kept.end(), [](const std::vector<size_t> *a, const std::vector<size_t> *b) { return a->size() > b->size(); });
+    for (const auto *members : kept) {
+        std::vector<size_t> idx = *members;
+        std::sort(idx.begin(), idx.end());
+        for (size_t i : idx) inliers.push_back(vehicle_inliers[i]);
+    }
     return inliers;
 }
 
@@ -522,6 +537,7 @@ struct SageICP {
     VoxelHashMap sem_map_;
     AdaptiveThreshold adaptive_threshold_;
     int threads_ = 1;
+    bool dynamic_cluster_order_ = false;  // PreprocessDynamic's cluster_order
     // oracle extras (diagnostics for parity tests)
     Cloud last_frame_downsample_;
     int last_iterations_ = 0;
@@ -558,7 +574,7 @@ struct SageICP {
         const Cloud cropped = config_.dynamic_vehicle_filter
                                   ? PreprocessDynamic(frame, config_.max_range, config_.min_range, config_.label_max_range,
                                                       config_.dynamic_vehicle_filter_th, config_.voxel_labels[(size_t)config_.dynamic_vehicle_voxid],
-                                                      config_.dynamic_remove_lankmark)
+                                                      config_.dynamic_remove_lankmark, dynamic_cluster_order_)
                                   : Preprocess(frame, config_.max_range, config_.min_range, config_.label_max_range);
         auto [source, frame_downsample] = Voxelize(cropped);
         const double sigma = GetAdaptiveThreshold();

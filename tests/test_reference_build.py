@@ -228,6 +228,28 @@ def test_dynamic_vehicle_filter_keeps_the_same_points(ref, orc, dy_th, seed):
     assert np.array_equal(key(a[n_plain:]), key(b[n_plain:]))
     if dy_th == 0.5:
         assert 0 < len(a) - n_plain
+    # with the oracle's cluster_order switch (clusters by descending size, input order inside a cluster) the ORDER matches as well
+    assert np.array_equal(a, orc.preprocess_dynamic(cfg, scan, cluster_order=True))
+
+
+def test_pipeline_with_the_dynamic_vehicle_filter(ref, orc):
+    """sageICP::RegisterFrame with dynamic_vehicle_filter = true (three of the four launch files): with the oracle emitting the
+    re-admitted vehicle points in the reference's cluster order, whole drives agree — query clouds identical, poses to rounding."""
+    from sage_icp_b200 import synthetic as syn
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config(dynamic_vehicle_filter=True)
+    rp, op = ref.RefPipeline(cfg), orc.OraclePipeline(cfg, evict_faithful=True)
+    op.set_dynamic_cluster_order(True)
+    traj = syn.trajectory(12)
+    for i in range(12):
+        scan = syn.make_scan(700 + i, tuple(traj[i]), n_beams=32, n_az=800)
+        pr = rp.register_frame(scan)
+        po, _, _ = op.register_frame(scan)
+        dt, da = pose_delta(pr, po)
+        assert dt < 1e-8 and da < 1e-9, (i, dt, da)
+        assert np.array_equal(rp.last_source(), op.last_source()), i
+    a, b = rp.local_map(), op.local_map()
+    assert a.shape == b.shape and np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a, b, atol=1e-7, rtol=0)
 
 
 def test_transform_to_last_frame(ref, orc, cfg):

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libsage_ref.so")
+LIB_PATH = os.environ.get("SAGE_REF_LIB") or os.path.join(_HERE, "_ref", "libsage_ref.so")  # override: experiments with other compiler flags
 REFERENCE_ROOT = "/root/reference/cpp"
 
 _dp = C.POINTER(C.c_double)

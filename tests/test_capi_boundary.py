@@ -266,3 +266,21 @@ def test_robin_tables_agree_when_the_new_element_itself_lands_at_the_limit(lib, 
     assert np.array_equal(got.astype(np.int64), want)
     got2, buckets2 = sg.robin_table_replay(np.c_[np.zeros(len(keys), np.int32), keys, np.zeros(len(keys), np.int32)])
     assert buckets2 == buckets == 1 << 15 and np.array_equal(got2, keys[want])
+
+
+def test_bad_config_is_refused_before_any_device_work(lib, cfg):
+    """sage_create validates the POD first (NULL arrays, negative lengths): a message, never a crash — also on a box without a GPU."""
+    L = lib
+    L.sage_create.restype = C.c_void_p
+    assert L.sage_create(None, 0) is None and b"NULL" in L.sage_last_error()
+    pod = cfg.to_pod()
+    keep = pod.group_labels
+    pod.group_labels = None
+    assert L.sage_create(C.byref(pod), 0) is None and b"group_labels" in L.sage_last_error()
+    pod.group_labels = keep
+    pod.n_basic_parts_labels = -1
+    assert L.sage_create(C.byref(pod), 0) is None and b"negative" in L.sage_last_error()
+    pod = cfg.to_pod()
+    keep = pod.voxel_size
+    pod.voxel_size = None
+    assert L.sage_create(C.byref(pod), 0) is None and b"voxel_size" in L.sage_last_error()

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_LIB_PATH = os.environ.get("SAGE_ORACLE_LIB") or os.path.join(_HERE, "liboracle.so")  # override: sanitizer builds
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -22,6 +22,8 @@ _lp = C.POINTER(C.c_int64)
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "sage_oracle.hpp", "robin_table.hpp", "se3.hpp", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if os.environ.get("SAGE_ORACLE_LIB"):
+        return _LIB_PATH
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH

@@ -155,12 +155,13 @@ int64_t sage_map_get_correspondences(sage_map *m, const double *xyzl, size_t n, 
                                      double th, double *target_out, uint8_t *matched_out);
 /* Exact neighbourhood statistics used for the algorithmic-bytes roofline figure. */
 int sage_map_nn_stats(sage_map *m, const double *xyzl, size_t n, uint64_t *occupied_voxels, uint64_t *candidates);
-/* Work the search kernels actually perform for these queries (one GetCorrespondences pass): 16-byte records scanned,
- * hash-table probes, queries whose f32 ranking was ambiguous and were re-ranked with the exact f64 scan, and queries the
- * thread-per-query kernel handed to the warp-per-query kernel (deferred_queries may be NULL). */
+/* Work the search kernels actually perform for these queries (one GetCorrespondences pass): 16-byte records ranked,
+ * hash-table probes, queries whose f32 ranking was ambiguous and were re-ranked with the exact f64 scan, queries the
+ * thread-per-query phase handed to a whole warp, and — tile search only, else 0 — records pulled into shared memory by TMA bulk
+ * copies (deferred_queries and staged_records may be NULL). */
 int sage_map_search_work(sage_map *m, const double *xyzl, size_t n, double max_correspondance_distance, double th,
                          uint64_t *records_scanned, uint64_t *table_probes, uint64_t *exact_queries,
-                         uint64_t *deferred_queries);
+                         uint64_t *deferred_queries, uint64_t *staged_records);
 
 /* sage_icp::RegisterFrame(frame, voxel_map, initial_guess, max_correspondence_distance, kernel, sem_th)
  * — core/Registration.cpp:113-141.  max_iterations / estimation_threshold default to the reference's constants

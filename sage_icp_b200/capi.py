@@ -221,13 +221,14 @@ class SageMap:
         self._chk(self.L.sage_map_nn_stats(self.h, _d(pts), C.c_size_t(len(pts)), C.byref(o), C.byref(c)), "sage_map_nn_stats")
         return int(o.value), int(c.value)
 
-    def search_work(self, pts, max_dist: float, th: float) -> Tuple[int, int, int, int]:
-        """(records scanned, table probes, queries re-ranked in f64, queries handed to the warp-per-query kernel) of one
-        correspondence pass."""
-        pts = _c64(pts); a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    def search_work(self, pts, max_dist: float, th: float, with_staged: bool = False):
+        """(records ranked, table probes, queries re-ranked in f64, queries finished by a whole warp[, records staged through
+        TMA bulk copies — tile search only]) of one correspondence pass."""
+        pts = _c64(pts); a, b, c, d, e = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._chk(self.L.sage_map_search_work(self.h, _d(pts), C.c_size_t(len(pts)), C.c_double(max_dist), C.c_double(th),
-                                              C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "sage_map_search_work")
-        return int(a.value), int(b.value), int(c.value), int(d.value)
+                                              C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)), "sage_map_search_work")
+        out = (int(a.value), int(b.value), int(c.value), int(d.value))
+        return out + (int(e.value),) if with_staged else out
 
     def normal_equations(self, pts, max_dist: float, kernel: float, sem_th: float):
         pts = _c64(pts); JTJ = np.zeros((6, 6)); JTr = np.zeros(6); n = C.c_int64()

@@ -373,14 +373,15 @@ int sage_map_nn_stats(sage_map *m, const double *xyzl, size_t n, uint64_t *occup
     });
 }
 int sage_map_search_work(sage_map *m, const double *xyzl, size_t n, double max_dist, double th, uint64_t *scanned, uint64_t *probes,
-                         uint64_t *exact, uint64_t *deferred) {
+                         uint64_t *exact, uint64_t *deferred, uint64_t *staged) {
     return (int)guarded([&] {
         need(scanned, "scanned"), need(probes, "probes"), need(exact, "exact");
         if (!xyzl && n) throw ArgError("null argument: xyzl");
-        unsigned long long a = 0, b = 0, c = 0, d = 0;
-        M(m).search_work(xyzl, n, max_dist, th, &a, &b, &c, &d);
+        unsigned long long a = 0, b = 0, c = 0, d = 0, e = 0;
+        M(m).search_work(xyzl, n, max_dist, th, &a, &b, &c, &d, &e);
         *scanned = a, *probes = b, *exact = c;
         if (deferred) *deferred = d;
+        if (staged) *staged = e;
         return 0;
     });
 }

@@ -173,6 +173,7 @@ struct IcpState {
     unsigned comm_error;  // fused peer exchange: a peer did not arrive in time
     unsigned long long stat_occupied, stat_candidates;
     unsigned long long stat_scanned, stat_probes, stat_exact, stat_heavy;  // search-kernel work counters (counting launches only)
+    unsigned long long stat_staged;  // tile search: records pulled into shared memory by bulk copies
 };
 
 }  // namespace sage

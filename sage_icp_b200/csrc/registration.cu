@@ -68,6 +68,10 @@ struct IterParams {
     double *xchg_peer[kMaxPeers];
     unsigned long long xchg_tag;
     int light_probes;  // neighbour probes a query may spend in the thread-per-query phase before it is deferred
+    // tile search (search_tile.cuh): unit boundaries in the sorted query array [n_units + 1], their number (device scalar), and
+    // the capacity of the block's staging area in 16-byte records
+    const uint32_t *tile_units, *tile_n_units, *tile_perm;  // tile_perm: sorted position -> index in the caller's array
+    uint32_t tile_stage_cap;
     unsigned long long *dbg;  // optional per-block timeline (tools/perf_probe.py): 4 globaltimer stamps per block + 4 global
 };
 
@@ -188,7 +192,7 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->done = (max_iters <= 0);
     st->ticket = 0;
     st->stat_occupied = st->stat_candidates = 0;
-    st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = 0;
+    st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = st->stat_staged = 0;
     st->comm_error = 0;
 }
 
@@ -448,6 +452,100 @@ __device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s
         st256(p.tgt_out + q, nb);
         p.matched_out[q] = ok ? 1 : 0;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// End of one Gauss-Newton iteration, shared by every search kernel: block-reduce the per-thread columns of s_acc (COLS columns,
+// a multiple of 32), publish the block's partials, elect the last block, which adds the partials of all blocks in a fixed order,
+// exchanges the sums with the other ranks (fused peer-memory all-reduce, `tag` = this iteration's sequence number) and takes the
+// Gauss-Newton step.  Called by every thread of the block.
+template <int COLS>
+__device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s_acc)[COLS], Pose &s_est, double &s_norm, int &s_last,
+                                                 unsigned long long tag) {
+    static_assert(COLS % 32 == 0, "whole warps of columns");
+    IcpState *st = p.st;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
+    // per-block partial sums: threads (fixed tree per sum) -> blocks (fixed order, by the last block to finish)
+    __syncthreads();
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x + 3] = gtime();
+    for (int k = warp; k < kSums; k += kWarps) {
+        double v = 0;
+#pragma unroll
+        for (int t = 0; t < COLS / 32; ++t) v += s_acc[k][lane + 32 * t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            p.partials[(size_t)k * gridDim.x + blockIdx.x] = v;  // [sum][block]
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x] = gtime();
+    // the last block adds the per-block partials: warp w owns sums w, w+W, w+2W, ...; lane l adds blocks l, l+32, ... in order
+    // (four loads in flight), then a fixed butterfly — the same tree for a given grid, so results are reproducible
+    for (int k = warp; k < kSums; k += kWarps) {
+        const double *pk = p.partials + (size_t)k * gridDim.x;
+        double v = 0;
+        uint32_t b = lane;
+        for (; b + 96 < gridDim.x; b += 128) {
+            const double a0 = __ldcg(pk + b), a1 = __ldcg(pk + b + 32), a2 = __ldcg(pk + b + 64), a3 = __ldcg(pk + b + 96);
+            v += a0, v += a1, v += a2, v += a3;
+        }
+        for (; b < gridDim.x; b += 32) v += __ldcg(pk + b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) st->sums[k] = v;
+    }
+    __syncthreads();
+    if (p.xchg_world > 1) {
+        // All-reduce of the 17 sums fused into this kernel: every rank's last block stores its sums, then the launch's tag,
+        // into its slot of EVERY peer's exchange buffer (plain stores over NVLink/NVSwitch peer mappings), waits until the
+        // slots of all ranks in its own buffer carry the tag, and adds them in rank order — the same values in the same
+        // order on every rank, so all replicas take the bit-identical Gauss-Newton step.  Slots alternate by tag parity: a
+        // rank can be at most one exchange ahead of a peer.  A peer that never shows up (2 s) ends the registration.
+        const int t = threadIdx.x;
+        const size_t slot = ((size_t)(tag & 1ull) * kMaxPeers) * kXchgSlot;
+        if (t < p.xchg_world) {
+            double *dst = p.xchg_peer[t] + slot + (size_t)p.xchg_rank * kXchgSlot;
+#pragma unroll
+            for (int k = 0; k < kSums; ++k) dst[k] = st->sums[k];
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(dst + kSums) = tag;
+        }
+        __syncthreads();
+        if (t < p.xchg_world) {
+            const volatile unsigned long long *flag =
+                reinterpret_cast<const volatile unsigned long long *>(p.xchg_peer[p.xchg_rank] + slot + (size_t)t * kXchgSlot + kSums);
+            const unsigned long long t0 = gtime();
+            while (*flag != tag) {
+                if (gtime() - t0 > 2000000000ull) {
+                    st->comm_error = 1;
+                    break;
+                }
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (t < kSums) {
+            const volatile double *mine = p.xchg_peer[p.xchg_rank] + slot;
+            double v = 0;
+            for (int r = 0; r < p.xchg_world; ++r) v += mine[(size_t)r * kXchgSlot + t];
+            st->sums[t] = v;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        st->ticket = 0;
+        if (p.dbg) p.dbg[kDbg * gridDim.x + 1] = gtime();
+        if (p.xchg_world > 1 && st->comm_error) st->done = 1;
+    }
+    __syncthreads();
+    if (p.solve && !(p.xchg_world > 1 && st->comm_error)) icp_step_block(st, &s_est, &s_norm, p.dbg ? p.dbg + kDbg * gridDim.x : nullptr);
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -780,20 +878,6 @@ __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
         if (pass + 1 < passes) __syncthreads();  // s_cnt / s_list are reused by the next pass
     }
 
-    // per-block partial sums: threads (fixed tree per sum) -> blocks (fixed order, by the last block to finish)
-    __syncthreads();
-    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x + 3] = gtime();
-    for (int k = warp; k < kSums; k += kWarps) {
-        double v = 0;
-#pragma unroll
-        for (int t = 0; t < kWarps; ++t) v += s_acc[k][lane + 32 * t];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-            p.partials[(size_t)k * gridDim.x + blockIdx.x] = v;  // [sum][block]
-            __threadfence();
-        }
-    }
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -809,73 +893,7 @@ __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
             atomicAdd(&st->stat_heavy, n_heavy);
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x] = gtime();
-    // the last block adds the per-block partials: warp w owns sums w, w+W, w+2W, ...; lane l adds blocks l, l+32, ... in order
-    // (four loads in flight), then a fixed butterfly — the same tree for a given grid, so results are reproducible
-    for (int k = warp; k < kSums; k += kWarps) {
-        const double *pk = p.partials + (size_t)k * gridDim.x;
-        double v = 0;
-        uint32_t b = lane;
-        for (; b + 96 < gridDim.x; b += 128) {
-            const double a0 = __ldcg(pk + b), a1 = __ldcg(pk + b + 32), a2 = __ldcg(pk + b + 64), a3 = __ldcg(pk + b + 96);
-            v += a0, v += a1, v += a2, v += a3;
-        }
-        for (; b < gridDim.x; b += 32) v += __ldcg(pk + b);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) st->sums[k] = v;
-    }
-    __syncthreads();
-    if (p.xchg_world > 1) {
-        // All-reduce of the 17 sums fused into this kernel: every rank's last block stores its sums, then the launch's tag,
-        // into its slot of EVERY peer's exchange buffer (plain stores over NVLink/NVSwitch peer mappings), waits until the
-        // slots of all ranks in its own buffer carry the tag, and adds them in rank order — the same values in the same
-        // order on every rank, so all replicas take the bit-identical Gauss-Newton step.  Slots alternate by tag parity: a
-        // rank can be at most one exchange ahead of a peer.  A peer that never shows up (2 s) ends the registration.
-        const int t = threadIdx.x;
-        const size_t slot = ((size_t)(p.xchg_tag & 1ull) * kMaxPeers) * kXchgSlot;
-        if (t < p.xchg_world) {
-            double *dst = p.xchg_peer[t] + slot + (size_t)p.xchg_rank * kXchgSlot;
-#pragma unroll
-            for (int k = 0; k < kSums; ++k) dst[k] = st->sums[k];
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long *>(dst + kSums) = p.xchg_tag;
-        }
-        __syncthreads();
-        if (t < p.xchg_world) {
-            const volatile unsigned long long *flag =
-                reinterpret_cast<const volatile unsigned long long *>(p.xchg_peer[p.xchg_rank] + slot + (size_t)t * kXchgSlot + kSums);
-            const unsigned long long t0 = gtime();
-            while (*flag != p.xchg_tag) {
-                if (gtime() - t0 > 2000000000ull) {
-                    st->comm_error = 1;
-                    break;
-                }
-            }
-            __threadfence_system();
-        }
-        __syncthreads();
-        if (t < kSums) {
-            const volatile double *mine = p.xchg_peer[p.xchg_rank] + slot;
-            double v = 0;
-            for (int r = 0; r < p.xchg_world; ++r) v += mine[(size_t)r * kXchgSlot + t];
-            st->sums[t] = v;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        st->ticket = 0;
-        if (p.dbg) p.dbg[kDbg * gridDim.x + 1] = gtime();
-        if (p.xchg_world > 1 && st->comm_error) st->done = 1;
-    }
-    __syncthreads();
-    if (p.solve && !(p.xchg_world > 1 && st->comm_error)) icp_step_block(st, &s_est, &s_norm, p.dbg ? p.dbg + kDbg * gridDim.x : nullptr);
-    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
+    finish_iteration<kNnThreads>(p, s_acc, s_est, s_norm, s_last, p.xchg_tag);
 }
 
 template <bool COUNT>
@@ -901,6 +919,10 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_persist
         if (*reinterpret_cast<volatile int *>(&p.st->done)) break;
     }
 }
+
+}  // namespace sage
+#include "search_tile.cuh"
+namespace sage {
 
 // Neighbourhood statistics for the algorithmic-bytes figure: per query, how many of the 27 voxels exist
 // and how many points they hold.  One thread per (query, voxel).
@@ -933,59 +955,99 @@ void VoxelMapGPU::profile_enable(bool on) {
     prof_used_ = 0;
 }
 
+// launches = Gauss-Newton iterations timed (a persistent launch counts every iteration it ran), ms = their total device time
 void VoxelMapGPU::profile_read(long long *launches, double *ms) {
     set_device();
     SAGE_CUDA(cudaStreamSynchronize(stream_));
     double total = 0;
+    long long iters = 0;
     for (size_t i = 0; i < prof_used_; ++i) {
         float t = 0;
         SAGE_CUDA(cudaEventElapsedTime(&t, prof_events_[i].first, prof_events_[i].second));
         total += t;
+        iters += prof_iters_[i];
     }
-    if (launches) *launches = (long long)prof_used_;
+    if (launches) *launches = iters;
     if (ms) *ms = total;
     prof_used_ = 0;
 }
 
-// one-time launch configuration of the search kernel (grid = co-resident blocks, tuning knobs from the environment)
-void VoxelMapGPU::init_search_config() {
-    if (nn_grid_ != 0) return;
-    {
-        int per_sm = 0;
-        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_search_kernel<false>, kNnThreads, 0));
-        nn_grid_ = sm_count_ * (per_sm > 0 ? per_sm : 1);
-        partials_.ensure((size_t)kSums * nn_grid_);
-        if (const char *e = getenv("SAGE_LIGHT_PROBES")) light_probes_ = atoi(e);  // tuning knobs
-        all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 3 / 4;
-        if (const char *e = getenv("SAGE_ALL_WARP_MAX")) all_warp_max_ = (size_t)atol(e);
-        if (getenv("SAGE_NO_ALL_WARP")) all_warp_max_ = 0;
-        if (const char *e = getenv("SAGE_POOLED")) pooled_ = atoi(e) != 0;  // experimental schedule, see nn_search_iteration
-        int coop = 0;
-        SAGE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
-        int per_sm_p = 0;
-        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, nn_search_persistent_kernel, kNnThreads, 0));
-        persistent_grid_ = sm_count_ * per_sm_p;
-        if (persistent_grid_ > nn_grid_) persistent_grid_ = nn_grid_;  // partials_ is sized for nn_grid_
-        if (persistent_grid_ < 1) coop = 0;
-        persistent_max_ = coop ? 20000 : 0;  // scans up to this many queries run their GN loop in one cooperative launch
-        if (const char *e = getenv("SAGE_PERSISTENT_MAX")) persistent_max_ = coop ? (size_t)atol(e) : 0;
+void VoxelMapGPU::prof_begin() {
+    if (!profile_) return;
+    if (prof_used_ == prof_events_.size()) {
+        cudaEvent_t a, b;
+        SAGE_CUDA(cudaEventCreate(&a));
+        SAGE_CUDA(cudaEventCreate(&b));
+        prof_events_.emplace_back(a, b);
+        prof_iters_.push_back(1);
     }
+    SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].first, stream_));
+}
+void VoxelMapGPU::prof_end(int iterations) {
+    if (!profile_) return;
+    SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].second, stream_));
+    prof_iters_[prof_used_] = iterations;
+    ++prof_used_;
 }
 
-// mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
-// as given; mode 2: as mode 1 with the search-work counters on.
-void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode,
-                                   double4 *tgt_out, uint8_t *matched_out, int persistent_iters) {
-    init_search_config();
-    // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
-    // there is a chunk for every block, fewer blocks for small scans
-    // small scans: one warp per query (all_warp) as long as that is at most two queries per resident warp
-    const bool all_warp = n <= all_warp_max_;
-    uint32_t grid = all_warp ? (uint32_t)((n + kNnThreads / 32 - 1) / (kNnThreads / 32)) : (uint32_t)((n + 31) / 32);
-    grid = grid < 1 ? 1 : (grid > (uint32_t)nn_grid_ ? (uint32_t)nn_grid_ : grid);
-    if (persistent_iters > 0 && grid > (uint32_t)persistent_grid_) grid = (uint32_t)persistent_grid_;  // must be co-resident
+static long env_long(const char *name, long dflt) {
+    const char *e = getenv(name);
+    return e ? atol(e) : dflt;
+}
 
-    IterParams p;
+// one-time launch configuration of the search kernels (grids = co-resident blocks, tuning knobs from the environment)
+void VoxelMapGPU::init_search_config() {
+    if (nn_grid_ != 0) return;
+    int per_sm = 0;
+    SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_search_kernel<false>, kNnThreads, 0));
+    nn_grid_ = sm_count_ * (per_sm > 0 ? per_sm : 1);
+    if (const char *e = getenv("SAGE_LIGHT_PROBES")) light_probes_ = atoi(e);  // tuning knobs
+    pooled_ = env_long("SAGE_POOLED", 0) != 0;  // experimental schedule, see nn_search_iteration
+    all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 3 / 4;
+    all_warp_max_ = (size_t)env_long("SAGE_ALL_WARP_MAX", (long)all_warp_max_);
+    if (getenv("SAGE_NO_ALL_WARP")) all_warp_max_ = 0;
+    int coop = 0;
+    SAGE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
+    int per_sm_p = 0;
+    SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, nn_search_persistent_kernel, kNnThreads, 0));
+    persistent_grid_ = sm_count_ * per_sm_p;
+    if (persistent_grid_ > nn_grid_) persistent_grid_ = nn_grid_;
+    if (persistent_grid_ < 1) coop = 0;
+    coop_ok_ = coop != 0;
+    persistent_max_ = coop ? 20000 : 0;  // scans up to this many queries run their GN loop in one cooperative launch
+    persistent_max_ = coop ? (size_t)env_long("SAGE_PERSISTENT_MAX", (long)persistent_max_) : 0;
+    // tile search: staging area (dynamic shared memory) + co-resident grid
+    static_assert(kTileThreads == 128, "tile_sort.cu cuts units of 128 queries");
+    tile_stage_cap_ = (uint32_t)env_long("SAGE_TILE_STAGE", 1536);  // records of 16 bytes: 24 KB
+    tile_minb_ = env_long("SAGE_TILE_MINB", 6) <= 4 ? 4 : 6;
+    const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
+    const void *k1 = tile_minb_ == 4 ? (const void *)nn_tile_kernel<4> : (const void *)nn_tile_kernel<6>;
+    const void *k2 = tile_minb_ == 4 ? (const void *)nn_tile_persistent_kernel<4> : (const void *)nn_tile_persistent_kernel<6>;
+    SAGE_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SAGE_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SAGE_CUDA(cudaFuncSetAttribute(nn_tile_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm_t = 0, per_sm_tp = 0;
+    if (tile_minb_ == 4) {
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, nn_tile_kernel<4>, kTileThreads, smem));
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tp, nn_tile_persistent_kernel<4>, kTileThreads, smem));
+    } else {
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, nn_tile_kernel<6>, kTileThreads, smem));
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tp, nn_tile_persistent_kernel<6>, kTileThreads, smem));
+    }
+    int per_sm_tile = per_sm_t < per_sm_tp ? per_sm_t : per_sm_tp;
+    const int want = (int)env_long("SAGE_TILE_BLOCKS", per_sm_tile);
+    if (want >= 1 && want < per_sm_tile) per_sm_tile = want;
+    tile_grid_ = sm_count_ * per_sm_tile;
+    tile_min_ = tile_grid_ > 0 ? (size_t)env_long("SAGE_TILE_MIN", 16384) : 0;
+    if (tile_grid_ > 0 && tile_min_ < 1) tile_min_ = 1;
+    if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
+    tile_probes_ = (int)env_long("SAGE_TILE_PROBES", 3);
+    tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
+    partials_.ensure((size_t)kSums * (nn_grid_ > tile_grid_ ? nn_grid_ : tile_grid_));
+}
+
+void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
+                              uint8_t *matched_out) {
     p.tbl = tbl_.p, p.mask = tbl_cap_ - 1, p.blk_pts = blk_pts_.p, p.blk_hot = blk_hot_.p, p.stride = stride_, p.voxel_size = voxel_size_;
     p.src = src, p.n = (uint32_t)n;
     p.max_dist = max_dist, p.kern = kernel, p.sem_th = sem_th;
@@ -1003,32 +1065,62 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         p.box_margin = (float)(32.0 * u * vsd);
     }
     p.st = icp_.p, p.partials = partials_.p, p.tgt_out = tgt_out, p.matched_out = matched_out;
+    p.dbg = nullptr;
+    p.light_probes = 8, p.all_warp = 0;
+    p.apply_est = (mode == 0), p.respect_done = (mode == 0);
+    p.solve = (mode == 0 && comm_ == nullptr);  // NCCL path: all-reduce and solve are separate launches
+    p.xchg_world = 1, p.xchg_rank = 0, p.xchg_tag = 0;
+    for (int k = 0; k < kMaxPeers; ++k) p.xchg_peer[k] = nullptr;
+    if (mode == 0 && peer_world_ > 1) {  // fused peer-memory all-reduce: the search kernel does everything
+        p.solve = 1;
+        p.xchg_world = peer_world_, p.xchg_rank = peer_rank_, p.xchg_tag = xchg_tag_ + 1;  // + iteration index (callers)
+        for (int k = 0; k < peer_world_; ++k) p.xchg_peer[k] = peer_buf_[k];
+    }
+    p.tile_units = tile_units_.p, p.tile_n_units = tile_nunits_.p, p.tile_perm = tile_vals_[1].p, p.tile_stage_cap = tile_stage_cap_;
+}
+
+// mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
+// as given; mode 2: as mode 1 with the search-work counters on.
+void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode,
+                                   double4 *tgt_out, uint8_t *matched_out, int persistent_iters, int iter_index) {
+    init_search_config();
+    if (mode != 0 && tile_min_ > 0 && n >= tile_min_) {
+        // correspondences / sums / work counters of the points as given, through the tile search: gather them in cell order
+        // (no transform), one nn_tile_kernel launch, results scattered back through the permutation
+        src_.ensure(n);
+        tile_prepare(src, n, pose_identity(), false);
+        IterParams p;
+        fill_params(p, src_.p, n, max_dist, kernel, sem_th, mode, tgt_out, matched_out);
+        p.light_probes = tile_probes_;
+        const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
+        if (mode == 2)
+            SAGE_LAUNCH((nn_tile_kernel<4, true>), tile_grid_, kTileThreads, smem, stream_, p, 1);
+        else if (tile_minb_ == 4)
+            SAGE_LAUNCH(nn_tile_kernel<4>, tile_grid_, kTileThreads, smem, stream_, p, 1);
+        else
+            SAGE_LAUNCH(nn_tile_kernel<6>, tile_grid_, kTileThreads, smem, stream_, p, 1);
+        return;
+    }
+    // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
+    // there is a chunk for every block, fewer blocks for small scans
+    // small scans: one warp per query (all_warp) as long as that is at most two queries per resident warp
+    const bool all_warp = n <= all_warp_max_;
+    uint32_t grid = all_warp ? (uint32_t)((n + kNnThreads / 32 - 1) / (kNnThreads / 32)) : (uint32_t)((n + 31) / 32);
+    grid = grid < 1 ? 1 : (grid > (uint32_t)nn_grid_ ? (uint32_t)nn_grid_ : grid);
+    if (persistent_iters > 0 && grid > (uint32_t)persistent_grid_) grid = (uint32_t)persistent_grid_;  // must be co-resident
+
+    IterParams p;
+    fill_params(p, src, n, max_dist, kernel, sem_th, mode, tgt_out, matched_out);
     p.dbg = (mode == 0 && dbg_on_) ? dbg_.p : nullptr;
     // Neighbour probes a query may spend in the thread-per-query phase before it is deferred to the warp phase: the fewer
     // queries there are, the more idle warps the deferred phase finds, so the earlier it pays to hand a query over
     // (measured on B200, profiles/r01g_nn_search_kernel_ncu.md: best of 1/2/3/5/8 at each size).
     const int auto_probes = n <= 20000 ? 1 : (n <= 90000 ? 3 : 8);
     p.light_probes = light_probes_ >= 0 ? light_probes_ : auto_probes, p.all_warp = all_warp ? 1 : 0;
-    p.apply_est = (mode == 0), p.respect_done = (mode == 0);
-    p.solve = (mode == 0 && comm_ == nullptr);  // NCCL path: all-reduce and solve are separate launches
-    p.xchg_world = 1, p.xchg_rank = 0, p.xchg_tag = 0;
-    for (int k = 0; k < kMaxPeers; ++k) p.xchg_peer[k] = nullptr;
-    if (mode == 0 && peer_world_ > 1) {  // fused peer-memory all-reduce: one launch per iteration does everything
-        p.solve = 1;
-        p.xchg_world = peer_world_, p.xchg_rank = peer_rank_, p.xchg_tag = ++xchg_tag_;
-        for (int k = 0; k < peer_world_; ++k) p.xchg_peer[k] = peer_buf_[k];
-    }
+    p.xchg_tag += (unsigned long long)iter_index;  // exchange number = exchanges completed so far + 1 + iteration
 
-    const bool prof = profile_ && mode == 0;
-    if (prof) {
-        if (prof_used_ == prof_events_.size()) {
-            cudaEvent_t a, b;
-            SAGE_CUDA(cudaEventCreate(&a));
-            SAGE_CUDA(cudaEventCreate(&b));
-            prof_events_.emplace_back(a, b);
-        }
-        SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].first, stream_));
-    }
+    const bool prof = mode == 0;
+    if (prof) prof_begin();
     if (persistent_iters > 0) {
         void *args[] = {&p, &persistent_iters};
         SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
@@ -1043,11 +1135,35 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     } else {
         SAGE_LAUNCH(nn_search_kernel<false>, grid, kNnThreads, 0, stream_, p);
     }
-    if (prof) {
-        SAGE_CUDA(cudaEventRecord(prof_events_[prof_used_].second, stream_));
-        ++prof_used_;
-    }
+    if (prof) prof_end(1);
     if (mode == 0 && comm_ != nullptr && peer_world_ <= 1) {
+        nccl_allreduce_sum_f64(comm_, icp_.p->sums, kSums, stream_);
+        SAGE_LAUNCH(icp_solve_kernel, 1, 64, 0, stream_, icp_.p);
+    }
+}
+
+// One Gauss-Newton iteration (persistent_iters == 0) or the whole loop (cooperative launch) of the tile search over src_, which
+// tile_prepare() has sorted, transformed by the initial guess and cut into units.
+void VoxelMapGPU::launch_tile(size_t n, double max_dist, double kernel, double sem_th, int iter_index, int persistent_iters) {
+    IterParams p;
+    fill_params(p, src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr);
+    p.light_probes = tile_probes_;
+    const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
+    prof_begin();
+    if (persistent_iters > 0) {
+        void *args[] = {&p, &persistent_iters};
+        const void *k = tile_minb_ == 4 ? (const void *)nn_tile_persistent_kernel<4> : (const void *)nn_tile_persistent_kernel<6>;
+        SAGE_CUDA(cudaLaunchCooperativeKernel(k, dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+        p.xchg_tag += (unsigned long long)iter_index;
+        if (tile_minb_ == 4)
+            SAGE_LAUNCH(nn_tile_kernel<4>, tile_grid_, kTileThreads, smem, stream_, p, iter_index == 0 ? 1 : 0);
+        else
+            SAGE_LAUNCH(nn_tile_kernel<6>, tile_grid_, kTileThreads, smem, stream_, p, iter_index == 0 ? 1 : 0);
+    }
+    prof_end(1);
+    if (comm_ != nullptr && peer_world_ <= 1) {
         nccl_allreduce_sum_f64(comm_, icp_.p->sums, kSums, stream_);
         SAGE_LAUNCH(icp_solve_kernel, 1, 64, 0, stream_, icp_.p);
     }
@@ -1066,29 +1182,50 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     icp_.ensure(1);
     icp_pin_.ensure(1);
     src_.ensure(n ? n : 1);
-    if (n) SAGE_CUDA(cudaMemcpyAsync(src_.p, frame, n * sizeof(double4), cudaMemcpyDeviceToDevice, stream_));
+    init_search_config();
+    // large scans: sort the queries by cell once, then the tile search (search_tile.cuh); the NCCL variant keeps its separate
+    // all-reduce + solve launches, so it cannot run the loop in one launch
+    const bool tile = tile_min_ > 0 && n >= tile_min_ && !dbg_on_;
+    if (tile)
+        tile_prepare(frame, n, guess, true);
+    else if (n)
+        SAGE_CUDA(cudaMemcpyAsync(src_.p, frame, n * sizeof(double4), cudaMemcpyDeviceToDevice, stream_));
     SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, guess, max_iters, est_th);
     // iterations are launched in batches (kernels of a finished registration return at once) and `done` is polled between
     // batches; the first batch is sized from the previous registration so that the common case needs one round trip
     int launched = 0;
-    // small scans, single rank: the whole loop in one cooperative launch (nn_search_persistent_kernel)
-    init_search_config();
-    if (n <= persistent_max_ && comm_ == nullptr && peer_world_ <= 1 && !dbg_on_) {
+    bool persistent = false;
+    if (tile && tile_persistent_ && comm_ == nullptr) {
+        launch_tile(n, max_dist, kernel, sem_th, 0, max_iters);
+        persistent = true;
+    } else if (!tile && n <= persistent_max_ && comm_ == nullptr && peer_world_ <= 1 && !dbg_on_) {
+        // small scans, single rank: the whole loop in one cooperative launch (nn_search_persistent_kernel)
         launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, max_iters);
+        persistent = true;
+    }
+    if (persistent) {
         SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
         SAGE_CUDA(cudaStreamSynchronize(stream_));
         launched = max_iters;
+        if (profile_ && prof_used_ > 0) prof_iters_[prof_used_ - 1] = icp_pin_.p->iter > 0 ? icp_pin_.p->iter : 1;
     }
     while (launched < max_iters) {
         int batch = launched == 0 ? (last_iters_ + 2 > 8 ? last_iters_ + 2 : 8) : 8;
         if (batch > 48) batch = 48;
         if (batch > max_iters - launched) batch = max_iters - launched;
-        for (int b = 0; b < batch; ++b) launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr);
+        for (int b = 0; b < batch; ++b) {
+            if (tile)
+                launch_tile(n, max_dist, kernel, sem_th, launched + b, 0);
+            else
+                launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, 0, launched + b);
+        }
         launched += batch;
         SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
         SAGE_CUDA(cudaStreamSynchronize(stream_));
         if (icp_pin_.p->done) break;
     }
+    // exchanges completed: every rank ran the same iterations (lock-step), whichever launch mode each of them chose
+    if (peer_world_ > 1) xchg_tag_ += (unsigned long long)icp_pin_.p->iter;
     if (icp_pin_.p->comm_error) throw CudaError("peer exchange timed out: a rank of the sharded registration did not arrive (nccl/peer)");
     pose_out = icp_pin_.p->result;
     last_iters_ = icp_pin_.p->iter;
@@ -1178,9 +1315,11 @@ size_t VoxelMapGPU::debug_timeline(unsigned long long *out, size_t cap) {
 }
 
 void VoxelMapGPU::search_work(const double *xyzl, size_t n, double max_dist, double sem_th, unsigned long long *scanned,
-                              unsigned long long *probes, unsigned long long *exact, unsigned long long *heavy) {
+                              unsigned long long *probes, unsigned long long *exact, unsigned long long *heavy, unsigned long long *staged) {
     set_device();
     *scanned = *probes = *exact = 0;
+    if (heavy) *heavy = 0;
+    if (staged) *staged = 0;
     if (n == 0 || empty()) return;
     double4 *d = stage_points(xyzl, n);
     icp_.ensure(1);
@@ -1191,6 +1330,7 @@ void VoxelMapGPU::search_work(const double *xyzl, size_t n, double max_dist, dou
     SAGE_CUDA(cudaStreamSynchronize(stream_));
     *scanned = icp_pin_.p->stat_scanned, *probes = icp_pin_.p->stat_probes, *exact = icp_pin_.p->stat_exact;
     if (heavy) *heavy = icp_pin_.p->stat_heavy;
+    if (staged) *staged = icp_pin_.p->stat_staged;
 }
 
 }  // namespace sage

@@ -1,0 +1,126 @@
+// Once per registration: order the queries of a large scan by the 2x2x2-voxel cell they fall in (under the initial guess) and cut
+// the ordered array into units for the tile search (search_tile.cuh).  The order is a locality hint only: the tile kernel
+// recomputes every unit's region from the queries' actual voxels each iteration, so a poor order costs time, never correctness.
+//
+//   tile_key_kernel     key = low 10 bits of each cell coordinate (cells repeat every 1024 cells = 1.6 km at 0.8 m voxels; two
+//                       aliasing cells in one run merely make a unit whose region does not fit, which falls back to global search)
+//   cub::DeviceRadixSort::SortPairs over the 30 key bits (stable, deterministic: equal inputs give equal unit lists, which is
+//                       what makes the sums reproducible run to run)
+//   tile_gather_kernel  src[j] = guess * frame[perm[j]] (or a plain gather for the correspondence-only entry points) — TransformPoints(initial_guess, source), core/Registration.cpp:122-123 —
+//                       and the per-tile count of unit heads (a new cell, or every kTileThreads-th position)
+//   tile_units_kernel   compaction of the heads into units[0..n_units], units[n_units] = n
+#include <cub/device/device_radix_sort.cuh>
+
+#include "voxel_map.cuh"
+
+namespace sage {
+
+constexpr int kUnitQueries = 128;  // = kTileThreads of search_tile.cuh (checked in registration.cu)
+constexpr int kHeadTile = 1024;    // positions per block of the head count / compaction kernels
+
+__global__ void tile_key_kernel(const double4 *__restrict__ frame, uint32_t n, Pose guess, int apply, double vs, uint32_t *__restrict__ keys,
+                                uint32_t *__restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 s = frame[i];
+    double x = s.x, y = s.y, z = s.z;
+    if (apply) pose_act(guess, s.x, s.y, s.z, x, y, z);
+    const int cx = trunc_div(x, vs) >> 1, cy = trunc_div(y, vs) >> 1, cz = trunc_div(z, vs) >> 1;  // arithmetic shift = floor
+    keys[i] = ((uint32_t)(cx & 1023) << 20) | ((uint32_t)(cy & 1023) << 10) | (uint32_t)(cz & 1023);
+    vals[i] = i;
+}
+
+__device__ __forceinline__ bool unit_head(const uint32_t *__restrict__ keys, uint32_t j) {
+    return j == 0 || (j % kUnitQueries) == 0 || keys[j] != keys[j - 1];
+}
+
+__global__ void __launch_bounds__(256) tile_gather_kernel(const double4 *__restrict__ frame, uint32_t n, Pose guess, int apply,
+                                                          const uint32_t *__restrict__ keys, const uint32_t *__restrict__ perm,
+                                                          double4 *__restrict__ src, uint32_t *__restrict__ tile_heads) {
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    uint32_t heads = 0;
+    for (uint32_t e = 0; e < kHeadTile / 256; ++e) {
+        const uint32_t j = blockIdx.x * kHeadTile + e * 256 + threadIdx.x;
+        if (j < n) {
+            const double4 s = frame[perm[j]];
+            double x = s.x, y = s.y, z = s.z;
+            if (apply) pose_act(guess, s.x, s.y, s.z, x, y, z);
+            src[j] = make_double4(x, y, z, s.w);
+            heads += unit_head(keys, j) ? 1u : 0u;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) heads += __shfl_xor_sync(0xffffffffu, heads, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, heads);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_heads[blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(256) tile_units_kernel(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ tile_heads,
+                                                         uint32_t *__restrict__ units, uint32_t *__restrict__ n_units) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    // heads in the tiles before this one
+    uint32_t before = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 256) before += tile_heads[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = before;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; ++w) t += s_warp[w];
+        s_base = t;
+    }
+    __syncthreads();
+    uint32_t base = s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t e = 0; e < kHeadTile / 256; ++e) {
+        const uint32_t j = blockIdx.x * kHeadTile + e * 256 + threadIdx.x;
+        const bool head = j < n && unit_head(keys, j);
+        const unsigned m = __ballot_sync(0xffffffffu, head);
+        __syncthreads();  // s_warp of the previous round has been read
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        uint32_t off = base + __popc(m & ((1u << lane) - 1u)), total = 0;
+        for (int w = 0; w < 8; ++w) {
+            off += w < warp ? s_warp[w] : 0u;
+            total += s_warp[w];
+        }
+        if (head) units[off] = j;
+        base += total;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        units[base] = n;
+        *n_units = base;
+    }
+}
+
+void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess, bool apply_guess) {
+    static_assert(kUnitQueries <= 128, "a unit is one pass of a tile block");
+    const uint32_t n32 = (uint32_t)n;
+    for (int k = 0; k < 2; ++k) {
+        tile_keys_[k].ensure(n);
+        tile_vals_[k].ensure(n);
+    }
+    tile_units_.ensure(n + 2);
+    const uint32_t tiles = (n32 + kHeadTile - 1) / kHeadTile;
+    tile_heads_.ensure(tiles + 1);
+    tile_nunits_.ensure(1);
+    size_t tmp_bytes = 0;
+    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, (int)n32, 0,
+                                              30, stream_));
+    tile_tmp_.ensure(tmp_bytes ? tmp_bytes : 1);
+    SAGE_LAUNCH(tile_key_kernel, (n32 + 255) / 256, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, voxel_size_, tile_keys_[0].p,
+                tile_vals_[0].p);
+    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(tile_tmp_.p, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, (int)n32, 0,
+                                              30, stream_));
+    g_launches.fetch_add(5, std::memory_order_relaxed);  // cub: one histogram + four onesweep passes (8-bit digits over 30 bits)
+    SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, tile_keys_[1].p, tile_vals_[1].p, src_.p,
+                tile_heads_.p);
+    SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_keys_[1].p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);
+}
+
+}  // namespace sage

@@ -9,6 +9,7 @@
 namespace sage {
 
 struct NcclComm;  // nccl_shim.cu
+struct IterParams;  // registration.cu
 
 // Raw device view handed to kernels.
 struct MapView {
@@ -96,7 +97,8 @@ public:
     void nn_stats(const double *xyzl, size_t n, unsigned long long *occupied, unsigned long long *candidates);
     // work the search kernel actually does on these queries: records scanned, table probes, queries re-ranked in f64
     void search_work(const double *xyzl, size_t n, double max_dist, double sem_th, unsigned long long *scanned,
-                     unsigned long long *probes, unsigned long long *exact, unsigned long long *heavy = nullptr);
+                     unsigned long long *probes, unsigned long long *exact, unsigned long long *heavy = nullptr,
+                     unsigned long long *staged = nullptr);
 
     cudaStream_t stream() const { return stream_; }
     int device() const { return device_; }
@@ -125,7 +127,15 @@ private:
     void reserve(size_t extra_points);  // make room for up to `extra_points` new voxels
     void rebuild_table(uint32_t new_cap);
     void launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
-                          uint8_t *matched_out, int persistent_iters = 0);
+                          uint8_t *matched_out, int persistent_iters = 0, int iter_index = 0);
+    void fill_params(IterParams &p, double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
+                     uint8_t *matched_out);
+    // tile search (search_tile.cuh, tile_sort.cu): sort + unit list once per registration, then one launch per iteration or one
+    // cooperative launch for the whole loop
+    void tile_prepare(const double4 *frame, size_t n, const Pose &guess, bool apply_guess);
+    void launch_tile(size_t n, double max_dist, double kernel, double sem_th, int iter_index, int persistent_iters);
+    void prof_begin();
+    void prof_end(int iterations);
     void init_search_config();
     void set_device() const { SAGE_CUDA(cudaSetDevice(device_)); }
 
@@ -174,6 +184,16 @@ private:
     int persistent_grid_ = 0;    // co-resident blocks of the persistent kernel
     size_t persistent_max_ = 0;  // scans up to this many queries run the whole GN loop in one cooperative launch
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
+    // tile search
+    DevBuf<uint32_t> tile_keys_[2], tile_vals_[2], tile_units_, tile_heads_, tile_nunits_;
+    DevBuf<uint8_t> tile_tmp_;
+    int tile_grid_ = 0;            // co-resident blocks of the tile kernels
+    int tile_minb_ = 6;            // which instantiation: 6 (80 registers) or 4 (128 registers) resident blocks per SM aimed at
+    size_t tile_min_ = 0;          // scans of at least this many queries take the tile search (0 = never)
+    uint32_t tile_stage_cap_ = 0;  // staging area of a block, in 16-byte records
+    int tile_probes_ = 3;          // occupied neighbour buckets a thread scans before its warp finishes the query
+    bool tile_persistent_ = true;  // whole GN loop in one cooperative launch
+    bool coop_ok_ = false;
     int light_probes_ = -1;  // < 0: chosen from the number of queries (launch_iteration); SAGE_LIGHT_PROBES overrides
     bool dbg_on_ = false;
     DevBuf<unsigned long long> dbg_;
@@ -181,6 +201,7 @@ private:
     // profiling
     bool profile_ = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events_;
+    std::vector<int> prof_iters_;  // Gauss-Newton iterations each timed launch ran (1, or the whole loop of a persistent launch)
     size_t prof_used_ = 0;
 
     NcclComm *comm_ = nullptr;

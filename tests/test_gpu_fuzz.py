@@ -6,7 +6,7 @@ import pytest
 
 from conftest import POSE_TOL_M, POSE_TOL_RAD, assert_maps_equal, pose_delta
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("search_mode")]
 
 LABEL_POOL = [0, 10, 11, 40, 44, 48, 49, 50, 51, 70, 71, 72, 80, 81, 99, 252]
 

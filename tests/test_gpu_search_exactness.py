@@ -4,7 +4,7 @@ the result must stay bit-identical to the oracle's plain f64 scan of all 27 voxe
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("search_mode")]
 
 BASIC_LABELS = [40, 44, 48, 49, 50, 70, 72]
 

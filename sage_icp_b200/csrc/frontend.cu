@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "frontend.cuh"
+#include "device_sort.cuh"
 
 namespace sage {
 
@@ -414,10 +415,35 @@ __global__ void dyn_flag_kernel(uint32_t n, const uint32_t *parent, const uint32
 
 __global__ void dyn_scatter_kernel(const double4 *in, uint32_t n, CropParams crop, const uint32_t *flags, const uint32_t *pos, double4 *out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 2 * n || !flags[t]) return;
-    double4 p = in[t < n ? t : t - n];
+    if (t >= n || !flags[t]) return;  // the plain inliers, input order
+    double4 p = in[t];
     crop_point(crop, p);  // re-applies the far-label zeroing
     out[pos[t]] = p;
+}
+
+// The reference appends the kept vehicle points cluster by cluster (core/Preprocessing.cpp:141-170) in the order PCL's
+// EuclideanClusterExtraction returns the clusters: by descending size, indices inside a cluster ascending (extractEuclideanClusters
+// sorts each cluster's indices, then sorts the clusters by size).  Equal sizes: discovery order, i.e. ascending smallest member —
+// which is this union-find's root.  Sort key of a kept vehicle point: (n - size, root); a stable sort keeps the index order inside a
+// cluster.  Points that are not kept get the bit above the key (they sort to the end and are not emitted).
+__global__ void dyn_sortkey_kernel(uint32_t n, const uint32_t *parent, const uint32_t *flags, const uint32_t *csize, int nbits, int end_bit,
+                                   unsigned long long *keys, uint32_t *vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = 1ull << end_bit;
+    if (flags[n + i]) {
+        const uint32_t r = dyn_root(parent, i);
+        k = ((unsigned long long)(n - csize[r]) << nbits) | r;
+    }
+    keys[i] = k, vals[i] = i;
+}
+__global__ void dyn_scatter_vehicle_kernel(const double4 *in, uint32_t n, CropParams crop, const unsigned long long *keys, const uint32_t *vals,
+                                           int end_bit, const uint32_t *pos, double4 *out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || (keys[j] >> end_bit)) return;
+    double4 p = in[vals[j]];
+    crop_point(crop, p);
+    out[pos[n] + j] = p;  // pos[n] = number of plain inliers (exclusive scan over [inlier flags | vehicle flags])
 }
 
 // one thread per point; fields may sit at any byte offset (the reference's message is a packed 17-byte record:
@@ -564,7 +590,20 @@ size_t FrontEnd::preprocess_dynamic(const double4 *in, size_t n, const CropParam
                 csize_.p, clm_.p, dyn.dy_th);
     SAGE_LAUNCH(dyn_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, nn, parent_.p, cls_.p, csize_.p, clm_.p, dyn.dy_th, flags_.p);
     scan_flags(2 * n, total_pin_.p, total_.p + 1);
-    SAGE_LAUNCH(dyn_scatter_kernel, fe_blocks(2 * n), kFeThreads, 0, stream_, in, nn, crop, flags_.p, pos_.p, out);
+    SAGE_LAUNCH(dyn_scatter_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, crop, flags_.p, pos_.p, out);
+    {
+        int nbits = 1;
+        while (((size_t)1 << nbits) < n) ++nbits;  // roots < n <= 2^nbits; n - size <= n < 2^(nbits + 1)
+        const int end_bit = 2 * nbits + 1;
+        dyn_key_[0].ensure(n), dyn_key_[1].ensure(n), dyn_val_[0].ensure(n), dyn_val_[1].ensure(n);
+        const size_t tmp = sort_pairs_tmp_bytes_u64(n, end_bit + 1);
+        sort_tmp_.ensure(tmp ? tmp : 1);
+        SAGE_LAUNCH(dyn_sortkey_kernel, fe_blocks(n), kFeThreads, 0, stream_, nn, parent_.p, flags_.p, csize_.p, nbits, end_bit, dyn_key_[0].p,
+                    dyn_val_[0].p);
+        g_launches.fetch_add(sort_pairs_u64(sort_tmp_.p, tmp, dyn_key_[0].p, dyn_key_[1].p, dyn_val_[0].p, dyn_val_[1].p, n, end_bit + 1, stream_),
+                             std::memory_order_relaxed);
+        SAGE_LAUNCH(dyn_scatter_vehicle_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, nn, crop, dyn_key_[1].p, dyn_val_[1].p, end_bit, pos_.p, out);
+    }
     SAGE_CUDA(cudaStreamSynchronize(stream_));
     if (total_pin_.p[1]) throw ArgError("Preprocess: point outside the +-2^20 cell range of the dynamic-vehicle filter");
     return total_pin_.p[0];

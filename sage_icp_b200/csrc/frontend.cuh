@@ -47,7 +47,9 @@ public:
     size_t preprocess(const double4 *in, size_t n, const CropParams &crop, double4 *out);
     // Preprocess with dynamic_vehicle_filter = true: range crop, then vehicle-labelled points survive only in clusters
     // (0.5 m single linkage, >= 5 points) that touch enough landmark-labelled points.  Non-vehicle inliers first (input
-    // order), kept vehicle points after them (input order).  Returns the kept count.  Synchronises.
+    // order), then the kept vehicle points cluster by cluster in the reference's order (clusters by descending size, then by
+    // smallest member; members ascending — core/Preprocessing.cpp:141-170 over PCL's cluster order).  Returns the kept
+    // count.  Synchronises.
     size_t preprocess_dynamic(const double4 *in, size_t n, const CropParams &crop, const DynFilterParams &dyn, double4 *out);
     // utils::PointCloud2ToEigen (ros/ros2/Utils.hpp:161-180) on the device: packed records -> x, y, z, label as f64
     void unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,
@@ -70,6 +72,9 @@ private:
     DevBuf<unsigned long long> cell_key_;
     DevBuf<uint32_t> cell_head_v_, cell_head_l_, next_v_, next_l_, parent_, csize_, clm_, cls_;
     uint32_t cell_cap_ = 0;
+    DevBuf<unsigned long long> dyn_key_[2];  // cluster-order sort of the kept vehicle points
+    DevBuf<uint32_t> dyn_val_[2];
+    DevBuf<uint8_t> sort_tmp_;
     PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_[2];
     int parity_ = 0;
     std::vector<std::vector<uint32_t>> group_members_, group_hashes_, group_order_;

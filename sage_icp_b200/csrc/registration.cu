@@ -1148,6 +1148,7 @@ void VoxelMapGPU::launch_tile(size_t n, double max_dist, double kernel, double s
     IterParams p;
     fill_params(p, src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr);
     p.light_probes = tile_probes_;
+    p.dbg = dbg_on_ ? dbg_.p : nullptr;
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
     prof_begin();
     if (persistent_iters > 0) {
@@ -1185,7 +1186,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     init_search_config();
     // large scans: sort the queries by cell once, then the tile search (search_tile.cuh); the NCCL variant keeps its separate
     // all-reduce + solve launches, so it cannot run the loop in one launch
-    const bool tile = tile_min_ > 0 && n >= tile_min_ && !dbg_on_;
+    const bool tile = tile_min_ > 0 && n >= tile_min_;
     if (tile)
         tile_prepare(frame, n, guess, true);
     else if (n)
@@ -1195,7 +1196,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     // batches; the first batch is sized from the previous registration so that the common case needs one round trip
     int launched = 0;
     bool persistent = false;
-    if (tile && tile_persistent_ && comm_ == nullptr) {
+    if (tile && tile_persistent_ && comm_ == nullptr && !dbg_on_) {
         launch_tile(n, max_dist, kernel, sem_th, 0, max_iters);
         persistent = true;
     } else if (!tile && n <= persistent_max_ && comm_ == nullptr && peer_world_ <= 1 && !dbg_on_) {
@@ -1309,7 +1310,8 @@ size_t VoxelMapGPU::debug_timeline(unsigned long long *out, size_t cap) {
     dbg_on_ = true;
     dbg_.ensure((size_t)kDbg * 4096 + 8);
     SAGE_CUDA(cudaStreamSynchronize(stream_));
-    const size_t n = (size_t)kDbg * (nn_grid_ > 0 ? nn_grid_ : 1) + 8;
+    const int g = nn_grid_ > tile_grid_ ? nn_grid_ : tile_grid_;
+    const size_t n = (size_t)kDbg * (g > 0 ? g : 1) + 8;
     if (out && cap >= n) SAGE_CUDA(cudaMemcpy(out, dbg_.p, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return n;
 }

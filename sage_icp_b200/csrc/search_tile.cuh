@@ -91,6 +91,7 @@ struct TileShared {
     int wbox[kTileWarps][6];
     uint32_t wsum[kTileWarps];
     unsigned long long mbar;
+    unsigned long long dbg_t[kDbg];  // development timeline (tools/tile_probe.py): time thread 0 spent in each phase, summed over units
 };
 
 // Warp-cooperative end of one query's search inside a staged region: the neighbours the thread phase left open, nearest box
@@ -171,6 +172,21 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     const float vs32 = p.vs32, th32 = p.th32;
     const uint32_t bar = smem_addr(&sh.mbar);
     const uint32_t n_units = *p.tile_n_units;
+    // development timeline: thread 0 adds the time since its previous stamp to phase k (the block barriers align the warps)
+    unsigned long long t_last = 0;
+    if (p.dbg && threadIdx.x == 0) {
+        for (int k = 0; k < kDbg; ++k) sh.dbg_t[k] = 0;
+        t_last = gtime();
+        sh.dbg_t[0] = t_last;
+    }
+#define TILE_STAMP(k)                             \
+    do {                                          \
+        if (p.dbg && threadIdx.x == 0) {          \
+            const unsigned long long t_ = gtime(); \
+            sh.dbg_t[k] += t_ - t_last;           \
+            t_last = t_;                          \
+        }                                         \
+    } while (0)
     unsigned long long n_ranked = 0, n_probes = 0, n_exact = 0, n_heavy = 0, n_staged = 0;  // work counters (COUNT launches only)
     for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
         const uint32_t ubeg = p.tile_units[u], uend = p.tile_units[u + 1];
@@ -212,6 +228,7 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                 }
             }
             __syncthreads();  // (1) boxes of all warps; the transformed points of this unit are visible to the block
+            TILE_STAMP(1);
             int lox = sh.wbox[0][0], loy = sh.wbox[0][1], loz = sh.wbox[0][2], hix = sh.wbox[0][3], hiy = sh.wbox[0][4], hiz = sh.wbox[0][5];
 #pragma unroll
             for (int w = 1; w < kTileWarps; ++w) {
@@ -269,9 +286,11 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                 for (int e = 0; e < 2; ++e)
                     if (staged[e]) bulk_g2s(smem_addr(stage + off[e]), p.blk_hot + g[e], c[e] * 16u, bar);
             }
+            TILE_STAMP(2);
             __syncthreads();  // (3) region table complete
             mbar_wait(bar, phase);  // every staged bucket has landed
             phase ^= 1u;
+            TILE_STAMP(3);
 
             // ---- D: thread per query against the staged region ---------------------------------------------------------------------
             uint32_t widx = kNil;
@@ -339,6 +358,7 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                         odd = true;
                 }
             }
+            TILE_STAMP(4);
             // ---- E: queries with many open neighbours, finished by their whole warp (lane = record) ---------------------------------
             {
                 unsigned hm = __ballot_sync(FULL, heavy);
@@ -356,6 +376,7 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                     if (COUNT && lane == 0) n_heavy += 1;
                 }
             }
+            TILE_STAMP(5);
             // ---- F: a unit whose region does not fit (never on a sorted scan): every query through the global-memory warp search ---
             if (!tiled) {
                 unsigned fm = __ballot_sync(FULL, fast);
@@ -380,6 +401,7 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                     if (COUNT && lane == 0) n_exact += 1;
                 }
             }
+            TILE_STAMP(6);
             // ---- H: acceptance on the exact records, residual, weight, the 16 sums + pair count --------------------------------------
             if (p.tgt_out != nullptr || __any_sync(FULL, widx != kNil)) {
                 double a[kSums];
@@ -419,9 +441,14 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                     for (int k = 0; k < kSums; ++k) sh.acc[k][threadIdx.x >> 2] += a[k];
                 }
             }
+            TILE_STAMP(7);
             __syncthreads();  // (4) region table, staging area and boxes are rewritten by the next unit
+            TILE_STAMP(8);
+            if (p.dbg && threadIdx.x == 0) sh.dbg_t[10] += 1, sh.dbg_t[11] += uend - c0 < (uint32_t)kTileThreads ? uend - c0 : kTileThreads;
         }
     }
+    if (p.dbg && threadIdx.x == 0) sh.dbg_t[9] = gtime();
+#undef TILE_STAMP
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -435,6 +462,8 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
         }
     }
     finish_iteration<kTileCols>(p, sh.acc, sh.est, sh.norm, sh.last, tag);
+    if (p.dbg && threadIdx.x == 0)  // after finish_iteration, which stamps slot 3 for the per-query kernels
+        for (int k = 0; k < kDbg; ++k) p.dbg[(size_t)kDbg * blockIdx.x + k] = sh.dbg_t[k];
 }
 
 // One launch = one Gauss-Newton iteration (`iteration0`: the first one of a registration).

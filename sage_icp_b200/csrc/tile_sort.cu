@@ -11,9 +11,34 @@
 //   tile_units_kernel   compaction of the heads into units[0..n_units], units[n_units] = n
 #include <cub/device/device_radix_sort.cuh>
 
+#include "device_sort.cuh"
 #include "voxel_map.cuh"
 
 namespace sage {
+
+// ---- device_sort.cuh -----------------------------------------------------------------------------------------------------------
+size_t sort_pairs_tmp_bytes_u32(size_t n, int end_bit) {
+    size_t b = 0;
+    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                              (int)n, 0, end_bit, (cudaStream_t) nullptr));
+    return b;
+}
+size_t sort_pairs_tmp_bytes_u64(size_t n, int end_bit) {
+    size_t b = 0;
+    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, b, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (const uint32_t *)nullptr,
+                                              (uint32_t *)nullptr, (int)n, 0, end_bit, (cudaStream_t) nullptr));
+    return b;
+}
+int sort_pairs_u32(void *tmp, size_t tmp_bytes, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, size_t n,
+                   int end_bit, cudaStream_t stream) {
+    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, stream));
+    return 1 + (end_bit + 7) / 8;  // one histogram + one onesweep pass per 8-bit digit
+}
+int sort_pairs_u64(void *tmp, size_t tmp_bytes, const unsigned long long *keys_in, unsigned long long *keys_out, const uint32_t *vals_in,
+                   uint32_t *vals_out, size_t n, int end_bit, cudaStream_t stream) {
+    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, stream));
+    return 1 + (end_bit + 7) / 8;
+}
 
 constexpr int kUnitQueries = 128;  // = kTileThreads of search_tile.cuh (checked in registration.cu)
 constexpr int kHeadTile = 1024;    // positions per block of the head count / compaction kernels
@@ -109,15 +134,12 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
     const uint32_t tiles = (n32 + kHeadTile - 1) / kHeadTile;
     tile_heads_.ensure(tiles + 1);
     tile_nunits_.ensure(1);
-    size_t tmp_bytes = 0;
-    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, (int)n32, 0,
-                                              30, stream_));
+    const size_t tmp_bytes = sort_pairs_tmp_bytes_u32(n, 30);
     tile_tmp_.ensure(tmp_bytes ? tmp_bytes : 1);
     SAGE_LAUNCH(tile_key_kernel, (n32 + 255) / 256, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, voxel_size_, tile_keys_[0].p,
                 tile_vals_[0].p);
-    SAGE_CUDA(cub::DeviceRadixSort::SortPairs(tile_tmp_.p, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, (int)n32, 0,
-                                              30, stream_));
-    g_launches.fetch_add(5, std::memory_order_relaxed);  // cub: one histogram + four onesweep passes (8-bit digits over 30 bits)
+    g_launches.fetch_add(sort_pairs_u32(tile_tmp_.p, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, n, 30, stream_),
+                         std::memory_order_relaxed);
     SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, tile_keys_[1].p, tile_vals_[1].p, src_.p,
                 tile_heads_.p);
     SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_keys_[1].p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);

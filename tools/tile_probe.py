@@ -55,3 +55,33 @@ for name in which:
         rows.append(row)
         print(json.dumps(row), flush=True)
     del m
+
+# per-block phase timeline of the tile kernel (one launch per iteration; the last of 3 iterations is what the buffer holds)
+if os.environ.get("TILE_TIMELINE", "1") != "0":
+    import ctypes as C
+    for k in KEYS:
+        os.environ.pop(k, None)
+    os.environ.update({"SAGE_TILE_MIN": "1"})
+    if len(sys.argv) > 4:
+        os.environ.update(dict(kv.split("=") for kv in sys.argv[4].split(",")))
+    m = sg.SageMap(0.8, 1e9, 20, 20, bench.BASIC_LABELS)
+    m.add_points(pts)
+    L = sg.load_library(); L.sage_debug_timeline.restype = C.c_size_t
+    m.register_frame(scan, guess, 3.0, 1 / 3, 0.4, max_iters=2, est_th=0.0)
+    n = L.sage_debug_timeline(m.h, None, C.c_size_t(0))
+    m.register_frame(scan, guess, 3.0, 1 / 3, 0.4, max_iters=3, est_th=0.0)
+    buf = np.zeros(n, np.uint64)
+    L.sage_debug_timeline(m.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_size_t(n))
+    K = 12
+    g = (n - 8) // K
+    b = buf[:K * g].reshape(g, K).astype(np.int64)
+    b = b[b[:, 0] > 0]
+    t0 = b[:, 0].min()
+    names = {1: "A load+transform+box", 2: "C probes+scan+issue", 3: "bulk wait", 4: "D thread phase", 5: "E warp phase", 6: "F/G fallback+exact",
+             7: "H accept+sums", 8: "end barrier"}
+    print(f"tile timeline: {len(b)} blocks, start spread {b[:,0].max()-t0} ns, block end (before finish) med {np.median(b[:,9]-t0):.0f} p90 "
+          f"{np.percentile(b[:,9]-t0,90):.0f} max {(b[:,9]-t0).max()} ns; units/block med {np.median(b[:,10]):.1f} max {b[:,10].max()}, "
+          f"queries/block med {np.median(b[:,11]):.0f} max {b[:,11].max()}")
+    for k, nm in names.items():
+        print(f"   {nm:24s}: per block total ns: median {np.median(b[:,k]):8.0f} p90 {np.percentile(b[:,k],90):8.0f} max {b[:,k].max():8d} | "
+              f"per unit mean {b[:,k].sum()/max(1,b[:,10].sum()):7.0f}")

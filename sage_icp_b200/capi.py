@@ -90,6 +90,17 @@ def _c64(a) -> np.ndarray:
     return a
 
 
+def _pts(a) -> np.ndarray:
+    """A cloud as the C ABI takes it: contiguous f64, n x 4 (x, y, z, label).  len() of the result is the point count handed to
+    the library, so anything that is not n x 4 is refused here rather than over-read there."""
+    a = _c64(a)
+    if a.ndim == 1 and a.size == 0:
+        return a.reshape(0, 4)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError(f"expected an (n, 4) array of x, y, z, label; got shape {a.shape}")
+    return a
+
+
 def device_count() -> int:
     return int(load_library().sage_device_count())
 
@@ -178,7 +189,7 @@ class SageMap:
     def num_points(self) -> int: return int(self._chk(self.L.sage_map_num_points(self.h), "sage_map_num_points"))
 
     def add_points(self, pts):
-        pts = _c64(pts)
+        pts = _pts(pts)
         self._chk(self.L.sage_map_add_points(self.h, _d(pts), C.c_size_t(len(pts))), "sage_map_add_points")
 
     def remove_far(self, origin):
@@ -186,7 +197,7 @@ class SageMap:
         self._chk(self.L.sage_map_remove_far(self.h, _d(o)), "sage_map_remove_far")
 
     def update(self, pts, pose):
-        pts, pose = _c64(pts), _c64(pose)
+        pts, pose = _pts(pts), _c64(pose)
         self._chk(self.L.sage_map_update(self.h, _d(pts), C.c_size_t(len(pts)), _d(pose)), "sage_map_update")
 
     def pointcloud(self) -> np.ndarray:
@@ -210,35 +221,35 @@ class SageMap:
 
     def get_correspondences(self, pts, max_dist: float, th: float):
         """Per-query result: (target (n,4), matched (n,) bool)."""
-        pts = _c64(pts); n = len(pts)
+        pts = _pts(pts); n = len(pts)
         tgt = np.zeros((n, 4)); matched = np.zeros(n, np.uint8)
         self._chk(self.L.sage_map_get_correspondences(self.h, _d(pts), C.c_size_t(n), C.c_double(max_dist), C.c_double(th), _d(tgt),
                                                       matched.ctypes.data_as(_u8p)), "sage_map_get_correspondences")
         return tgt, matched.astype(bool)
 
     def nn_stats(self, pts) -> Tuple[int, int]:
-        pts = _c64(pts); o, c = C.c_uint64(), C.c_uint64()
+        pts = _pts(pts); o, c = C.c_uint64(), C.c_uint64()
         self._chk(self.L.sage_map_nn_stats(self.h, _d(pts), C.c_size_t(len(pts)), C.byref(o), C.byref(c)), "sage_map_nn_stats")
         return int(o.value), int(c.value)
 
     def search_work(self, pts, max_dist: float, th: float, with_staged: bool = False):
         """(records ranked, table probes, queries re-ranked in f64, queries finished by a whole warp[, records staged through
         TMA bulk copies — tile search only]) of one correspondence pass."""
-        pts = _c64(pts); a, b, c, d, e = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        pts = _pts(pts); a, b, c, d, e = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._chk(self.L.sage_map_search_work(self.h, _d(pts), C.c_size_t(len(pts)), C.c_double(max_dist), C.c_double(th),
                                               C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e)), "sage_map_search_work")
         out = (int(a.value), int(b.value), int(c.value), int(d.value))
         return out + (int(e.value),) if with_staged else out
 
     def normal_equations(self, pts, max_dist: float, kernel: float, sem_th: float):
-        pts = _c64(pts); JTJ = np.zeros((6, 6)); JTr = np.zeros(6); n = C.c_int64()
+        pts = _pts(pts); JTJ = np.zeros((6, 6)); JTr = np.zeros(6); n = C.c_int64()
         self._chk(self.L.sage_core_normal_equations(self.h, _d(pts), C.c_size_t(len(pts)), C.c_double(max_dist), C.c_double(kernel),
                                                     C.c_double(sem_th), _d(JTJ), _d(JTr), C.byref(n)), "sage_core_normal_equations")
         return JTJ, JTr, int(n.value)
 
     def register_frame(self, frame, guess, max_dist: float, kernel: float, sem_th: float, max_iters: int = 0, est_th: float = -1.0):
         """sage_icp::RegisterFrame (core/Registration.cpp:113-141) with HOST buffers.  Returns (pose7, iterations)."""
-        frame, guess = _c64(frame), _c64(guess); out = np.empty(7); it = C.c_int()
+        frame, guess = _pts(frame), _c64(guess); out = np.empty(7); it = C.c_int()
         self._chk(self.L.sage_core_register_frame(self.h, _d(frame), C.c_size_t(len(frame)), _d(guess), C.c_double(max_dist),
                                                   C.c_double(kernel), C.c_double(sem_th), max_iters, C.c_double(est_th), _d(out),
                                                   C.byref(it)), "sage_core_register_frame")
@@ -311,7 +322,7 @@ class SagePipeline:
 
     def register_frame(self, pts, timestamps=None):
         """RegisterFrame(frame[, timestamps]) -> (pose7, t_icp, t_all); `source` via last_source()."""
-        pts = _c64(pts); pose = np.empty(7); ti, ta = C.c_double(), C.c_double()
+        pts = _pts(pts); pose = np.empty(7); ti, ta = C.c_double(), C.c_double()
         ts = None if timestamps is None else _d(_c64(timestamps))
         self._chk(self.L.sage_register_frame(self.h, _d(pts), C.c_size_t(len(pts)), ts, _d(pose), C.byref(ti), C.byref(ta)),
                   "sage_register_frame")
@@ -347,23 +358,23 @@ class SagePipeline:
         out = np.empty(7); self.L.sage_get_prediction_model(self.h, _d(out)); return out
 
     def voxelize(self, pts):
-        pts = _c64(pts); s, d = np.empty_like(pts), np.empty_like(pts); ns, nd = C.c_size_t(), C.c_size_t()
+        pts = _pts(pts); s, d = np.empty_like(pts), np.empty_like(pts); ns, nd = C.c_size_t(), C.c_size_t()
         self._chk(self.L.sage_voxelize(self.h, _d(pts), C.c_size_t(len(pts)), _d(s), C.byref(ns), _d(d), C.byref(nd)), "sage_voxelize")
         return s[:ns.value].copy(), d[:nd.value].copy()
 
     def preprocess(self, pts):
-        pts = _c64(pts); out = np.empty_like(pts)
+        pts = _pts(pts); out = np.empty_like(pts)
         n = self._chk(self.L.sage_preprocess(self.h, _d(pts), C.c_size_t(len(pts)), _d(out), C.c_size_t(len(pts))), "sage_preprocess")
         return out[:n].copy()
 
     def voxel_downsample(self, pts, vox_scale: float):
-        pts = _c64(pts); out = np.empty_like(pts)
+        pts = _pts(pts); out = np.empty_like(pts)
         n = self._chk(self.L.sage_voxel_downsample(self.h, _d(pts), C.c_size_t(len(pts)), C.c_double(vox_scale), _d(out),
                                                    C.c_size_t(len(pts))), "sage_voxel_downsample")
         return out[:n].copy()
 
     def transform_to_last_frame(self, last_pose, current_pose, pts):
-        last_pose, current_pose, pts = _c64(last_pose), _c64(current_pose), _c64(pts); out = np.empty_like(pts)
+        last_pose, current_pose, pts = _c64(last_pose), _c64(current_pose), _pts(pts); out = np.empty_like(pts)
         self.L.sage_transform_to_last_frame(self.h, _d(last_pose), _d(current_pose), _d(pts), C.c_size_t(len(pts)), _d(out))
         return out
 

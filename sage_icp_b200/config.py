@@ -64,6 +64,10 @@ class SageConfig:
 
     def to_pod(self) -> ConfigPOD:
         """Build the POD; the backing arrays are kept alive on the returned object (``_keep``)."""
+        if len(self.voxel_labels) != len(self.voxel_size):
+            # n_groups is taken from voxel_size and the offsets from voxel_labels: a mismatch would make the library read past
+            # the offsets array (the C++ adaptor rejects it the same way)
+            raise ValueError(f"voxel_labels has {len(self.voxel_labels)} groups but voxel_size has {len(self.voxel_size)} entries")
         offs = [0]
         flat: List[int] = []
         for g in self.voxel_labels:

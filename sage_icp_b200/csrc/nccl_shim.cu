@@ -47,7 +47,12 @@ Api &api() {
     a.CommDestroy = (CommDestroy_t)dlsym(a.h, "ncclCommDestroy");
     a.AllReduce = (AllReduce_t)dlsym(a.h, "ncclAllReduce");
     a.GetErrorString = (GetErrorString_t)dlsym(a.h, "ncclGetErrorString");
-    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce) throw NcclError("libnccl lacks required symbols");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce) {
+        // leave no half-initialised table behind: the next call must run the symbol check again, not call through a null pointer
+        dlclose(a.h);
+        a = Api{};
+        throw NcclError("libnccl lacks required symbols");
+    }
     return a;
 }
 void check(int rc, const char *what) {

@@ -67,6 +67,7 @@ struct IterParams {
     int xchg_world, xchg_rank;
     double *xchg_peer[kMaxPeers];
     unsigned long long xchg_tag;
+    unsigned long long xchg_timeout_ns;  // how long the last block waits for the slowest rank before it gives up (comm_error)
     int light_probes;  // neighbour probes a query may spend in the thread-per-query phase before it is deferred
     // tile search (search_tile.cuh): unit boundaries in the sorted query array [n_units + 1], their number (device scalar), and
     // the capacity of the block's staging area in 16-byte records
@@ -135,7 +136,15 @@ __device__ __noinline__ void icp_solve_xi(const double *S, double xi[6]) {
     const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
     const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
     const double det = m00 * c00 + m01 * c01 + m02 * c02;
-    if (det == 0.0 || !(det == det)) return;
+    // Rank-deficient rotation block (one or two correspondences, collinear points: track loss, a scan leaving the map): det is
+    // rounding noise there, not 0, and dividing by it would throw the pose far away.  The reference's LDLT divides by whatever
+    // pivot rounding leaves (Eigen zeroes only pivots below 1/highest()), so its step is noise-dominated too; here the step
+    // degrades to the translation that aligns the weighted centroids (o = 0, u = b_t / w), which is bounded by the residuals.
+    const double tr = (m00 + m11 + m22) * (1.0 / 3.0);
+    if (!(fabs(det) > 1e-12 * tr * tr * tr)) {
+        xi[0] = btx * iw, xi[1] = bty * iw, xi[2] = btz * iw;
+        return;
+    }
     const double id = 1.0 / det;
     const double ox = (c00 * qx + c01 * qy + c02 * qz) * id, oy = (c01 * qx + c11 * qy + c12 * qz) * id, oz = (c02 * qx + c12 * qy + c22 * qz) * id;
     // u = (b_t - o x s) / w
@@ -506,7 +515,8 @@ __device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s
         // into its slot of EVERY peer's exchange buffer (plain stores over NVLink/NVSwitch peer mappings), waits until the
         // slots of all ranks in its own buffer carry the tag, and adds them in rank order — the same values in the same
         // order on every rank, so all replicas take the bit-identical Gauss-Newton step.  Slots alternate by tag parity: a
-        // rank can be at most one exchange ahead of a peer.  A peer that never shows up (2 s) ends the registration.
+        // rank can be at most one exchange ahead of a peer.  A peer that never shows up (xchg_timeout_ns, default 30 s: ranks are
+        // independent processes whose launches can drift apart by a module load or an allocation) ends the registration.
         const int t = threadIdx.x;
         const size_t slot = ((size_t)(tag & 1ull) * kMaxPeers) * kXchgSlot;
         if (t < p.xchg_world) {
@@ -522,7 +532,7 @@ __device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s
                 reinterpret_cast<const volatile unsigned long long *>(p.xchg_peer[p.xchg_rank] + slot + (size_t)t * kXchgSlot + kSums);
             const unsigned long long t0 = gtime();
             while (*flag != tag) {
-                if (gtime() - t0 > 2000000000ull) {
+                if (gtime() - t0 > p.xchg_timeout_ns) {
                     st->comm_error = 1;
                     break;
                 }
@@ -1043,6 +1053,10 @@ void VoxelMapGPU::init_search_config() {
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_probes_ = (int)env_long("SAGE_TILE_PROBES", 3);
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
+    {
+        const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
+        xchg_timeout_ns_ = (unsigned long long)(t < 1 ? 1 : t) * 1000000000ull;
+    }
     partials_.ensure((size_t)kSums * (nn_grid_ > tile_grid_ ? nn_grid_ : tile_grid_));
 }
 
@@ -1069,7 +1083,7 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
     p.light_probes = 8, p.all_warp = 0;
     p.apply_est = (mode == 0), p.respect_done = (mode == 0);
     p.solve = (mode == 0 && comm_ == nullptr);  // NCCL path: all-reduce and solve are separate launches
-    p.xchg_world = 1, p.xchg_rank = 0, p.xchg_tag = 0;
+    p.xchg_world = 1, p.xchg_rank = 0, p.xchg_tag = 0, p.xchg_timeout_ns = xchg_timeout_ns_;
     for (int k = 0; k < kMaxPeers; ++k) p.xchg_peer[k] = nullptr;
     if (mode == 0 && peer_world_ > 1) {  // fused peer-memory all-reduce: the search kernel does everything
         p.solve = 1;
@@ -1227,7 +1241,13 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     }
     // exchanges completed: every rank ran the same iterations (lock-step), whichever launch mode each of them chose
     if (peer_world_ > 1) xchg_tag_ += (unsigned long long)icp_pin_.p->iter;
-    if (icp_pin_.p->comm_error) throw CudaError("peer exchange timed out: a rank of the sharded registration did not arrive (nccl/peer)");
+    if (icp_pin_.p->comm_error) {
+        // the exchange sequence numbers of the ranks no longer agree: drop the mappings so that the next registration fails
+        // loudly ("not attached") instead of deadlocking; every rank has to attach again (sage_map_comm_peer_attach)
+        peer_detach();
+        throw CudaError("peer exchange timed out: a rank of the sharded registration did not arrive; the peer communicator was detached, "
+                        "re-attach on every rank (SAGE_XCHG_TIMEOUT_S sets the wait, default 30 s)");
+    }
     pose_out = icp_pin_.p->result;
     last_iters_ = icp_pin_.p->iter;
     return icp_pin_.p->iter;

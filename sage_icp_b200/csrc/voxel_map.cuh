@@ -208,7 +208,8 @@ private:
     double *peer_buf_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [rank] -> mapped exchange buffer
     double *xchg_local_ = nullptr;
     int peer_rank_ = 0, peer_world_ = 0;
-    unsigned long long xchg_tag_ = 0;
+    unsigned long long xchg_tag_ = 0;                       // exchanges completed (same on every rank)
+    unsigned long long xchg_timeout_ns_ = 30000000000ull;  // SAGE_XCHG_TIMEOUT_S
 };
 
 }  // namespace sage

@@ -63,3 +63,26 @@ def test_register_frame_drive_equals_the_reference(ref):
     assert worst < 1e-6
     a, b = gp.local_map(), rp.local_map()
     assert a.shape == b.shape and np.array_equal(a[:, 3], b[:, 3]) and np.allclose(a, b, atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("overrides", [dict(), dict(voxel_size_map=1.0, sem_th=0.8), dict(sem_th=0.2)], ids=["odometry", "odometry_360", "odometry_raw"])
+def test_dynamic_vehicle_filter_drive_equals_the_reference(ref, overrides):
+    """dynamic_vehicle_filter = true (default in three of the four launch files): the reference's own Preprocess — cluster by
+    cluster emission over the stand-in PCL — vs the CUDA front end, frame by frame: identical filtered clouds in order, identical
+    query clouds, poses within tolerance (core/Preprocessing.cpp:95-172)."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config(dynamic_vehicle_filter=True, **overrides)
+    gp, rp = sg.SagePipeline(cfg), ref.RefPipeline(cfg)
+    n = 12
+    traj = syn.trajectory(n)
+    for i in range(n):
+        scan = syn.make_scan(700 + i, tuple(traj[i]), n_beams=48, n_az=1000)
+        if i < 3:
+            assert np.array_equal(gp.preprocess(scan), ref.preprocess(cfg, scan)), i
+        pg, _, _ = gp.register_frame(scan)
+        pr = rp.register_frame(scan)
+        dt, da = pose_delta(pg, pr)
+        assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (i, dt, da)
+        assert np.array_equal(gp.last_source(), rp.last_source()), i

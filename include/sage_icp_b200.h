@@ -194,9 +194,12 @@ int64_t sage_voxel_downsample(sage_pipeline *h, const double *xyzl, size_t n, do
 /* The CUDA stream (cudaStream_t) the map's kernels are launched on, for event timing by the caller. */
 void *sage_map_stream(sage_map *m);
 /* Per-kernel CUDA-event timing of the correspondence+normal-equation kernel.  enable=1 records an event pair around
- * every launch; sage_map_profile_read() synchronises, returns launches and total milliseconds since the last read. */
+ * every launch; sage_map_profile_read() synchronises, returns the Gauss-Newton iterations those launches ran (a launch runs one
+ * iteration, or — the cooperative kernels — the whole loop of a registration) and their total milliseconds since the last
+ * read; sage_map_profile_read_launches() also returns the number of launches. */
 int sage_map_profile_enable(sage_map *m, int enable);
-int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms);
+int sage_map_profile_read(sage_map *m, int64_t *iterations, double *total_ms);
+int sage_map_profile_read_launches(sage_map *m, int64_t *iterations, int64_t *launches, double *total_ms);
 /* Total kernel launches issued by this library in the calling process since load (bench.py's gpu_launches). */
 int64_t sage_launch_count(void);
 

@@ -270,9 +270,16 @@ class SageMap:
     def profile_enable(self, on: bool): self.L.sage_map_profile_enable(self.h, int(on))
 
     def profile_read(self) -> Tuple[int, float]:
+        """(Gauss-Newton iterations timed, their total device milliseconds) since the last read."""
         n, ms = C.c_int64(), C.c_double()
         self._chk(self.L.sage_map_profile_read(self.h, C.byref(n), C.byref(ms)), "sage_map_profile_read")
         return int(n.value), float(ms.value)
+
+    def profile_read_launches(self) -> Tuple[int, int, float]:
+        """(iterations, kernel launches, total device milliseconds): a cooperative launch runs a whole registration's loop."""
+        n, k, ms = C.c_int64(), C.c_int64(), C.c_double()
+        self._chk(self.L.sage_map_profile_read_launches(self.h, C.byref(n), C.byref(k), C.byref(ms)), "sage_map_profile_read_launches")
+        return int(n.value), int(k.value), float(ms.value)
 
     def comm_init(self, rank: int, world: int, uid: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)

@@ -430,12 +430,23 @@ int sage_map_profile_enable(sage_map *m, int enable) {
         return 0;
     });
 }
-int sage_map_profile_read(sage_map *m, int64_t *launches, double *total_ms) {
+int sage_map_profile_read(sage_map *m, int64_t *iterations, double *total_ms) {
     return (int)guarded([&] {
-        long long l = 0;
+        long long l = 0, k = 0;
         double ms = 0;
-        M(m).profile_read(&l, &ms);
-        if (launches) *launches = l;
+        M(m).profile_read(&l, &ms, &k);
+        if (iterations) *iterations = l;
+        if (total_ms) *total_ms = ms;
+        return 0;
+    });
+}
+int sage_map_profile_read_launches(sage_map *m, int64_t *iterations, int64_t *launches, double *total_ms) {
+    return (int)guarded([&] {
+        long long l = 0, k = 0;
+        double ms = 0;
+        M(m).profile_read(&l, &ms, &k);
+        if (iterations) *iterations = l;
+        if (launches) *launches = k;
         if (total_ms) *total_ms = ms;
         return 0;
     });

@@ -170,6 +170,7 @@ struct IcpState {
     int iter;         // iterations executed
     int done;
     unsigned ticket;  // last-block election
+    unsigned unit_next;  // tile search: units handed out so far in this registration (never reset inside one, see search_tile.cuh)
     unsigned comm_error;  // fused peer exchange: a peer did not arrive in time
     unsigned long long stat_occupied, stat_candidates;
     unsigned long long stat_scanned, stat_probes, stat_exact, stat_heavy;  // search-kernel work counters (counting launches only)

@@ -72,6 +72,8 @@ struct IterParams {
     // tile search (search_tile.cuh): unit boundaries in the sorted query array [n_units + 1], their number (device scalar), and
     // the capacity of the block's staging area in 16-byte records
     const uint32_t *tile_units, *tile_n_units, *tile_perm;  // tile_perm: sorted position -> index in the caller's array
+    double *tile_unit_part;    // [unit][17]
+    uint32_t *tile_group_cnt;  // [group]
     uint32_t tile_stage_cap;
     unsigned long long *dbg;  // optional per-block timeline (tools/perf_probe.py): 4 globaltimer stamps per block + 4 global
 };
@@ -200,6 +202,7 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->iter = 0;
     st->done = (max_iters <= 0);
     st->ticket = 0;
+    st->unit_next = 0;
     st->stat_occupied = st->stat_candidates = 0;
     st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = st->stat_staged = 0;
     st->comm_error = 0;
@@ -464,47 +467,25 @@ __device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s
 }
 
 // ---------------------------------------------------------------------------------------------
-// End of one Gauss-Newton iteration, shared by every search kernel: block-reduce the per-thread columns of s_acc (COLS columns,
-// a multiple of 32), publish the block's partials, elect the last block, which adds the partials of all blocks in a fixed order,
-// exchanges the sums with the other ranks (fused peer-memory all-reduce, `tag` = this iteration's sequence number) and takes the
-// Gauss-Newton step.  Called by every thread of the block.
-template <int COLS>
-__device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s_acc)[COLS], Pose &s_est, double &s_norm, int &s_last,
-                                                 unsigned long long tag) {
-    static_assert(COLS % 32 == 0, "whole warps of columns");
+// The part of an iteration that ONE block runs once every partial sum is published: add the `count` partials of each sum in a
+// fixed order (p.partials[k * count + i]), exchange the sums with the other ranks (fused peer-memory all-reduce, `tag` = this
+// iteration's sequence number), take the Gauss-Newton step.  Called by every thread of that block.
+__device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t count, Pose &s_est, double &s_norm, unsigned long long tag) {
     IcpState *st = p.st;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
-    // per-block partial sums: threads (fixed tree per sum) -> blocks (fixed order, by the last block to finish)
-    __syncthreads();
-    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x + 3] = gtime();
-    for (int k = warp; k < kSums; k += kWarps) {
-        double v = 0;
-#pragma unroll
-        for (int t = 0; t < COLS / 32; ++t) v += s_acc[k][lane + 32 * t];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) {
-            p.partials[(size_t)k * gridDim.x + blockIdx.x] = v;  // [sum][block]
-            __threadfence();
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
     __threadfence();
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x] = gtime();
     // the last block adds the per-block partials: warp w owns sums w, w+W, w+2W, ...; lane l adds blocks l, l+32, ... in order
     // (four loads in flight), then a fixed butterfly — the same tree for a given grid, so results are reproducible
     for (int k = warp; k < kSums; k += kWarps) {
-        const double *pk = p.partials + (size_t)k * gridDim.x;
+        const double *pk = p.partials + (size_t)k * count;
         double v = 0;
         uint32_t b = lane;
-        for (; b + 96 < gridDim.x; b += 128) {
+        for (; b + 96 < count; b += 128) {
             const double a0 = __ldcg(pk + b), a1 = __ldcg(pk + b + 32), a2 = __ldcg(pk + b + 64), a3 = __ldcg(pk + b + 96);
             v += a0, v += a1, v += a2, v += a3;
         }
-        for (; b < gridDim.x; b += 32) v += __ldcg(pk + b);
+        for (; b < count; b += 32) v += __ldcg(pk + b);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) st->sums[k] = v;
@@ -558,6 +539,36 @@ __device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
 }
 
+
+// End of one Gauss-Newton iteration for the kernels whose blocks keep running sums: block-reduce the per-thread columns of s_acc
+// (COLS columns, a multiple of 32), publish the block's partials, elect the last block to finish, which runs reduce_and_step.
+template <int COLS>
+__device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s_acc)[COLS], Pose &s_est, double &s_norm, int &s_last,
+                                                 unsigned long long tag) {
+    static_assert(COLS % 32 == 0, "whole warps of columns");
+    IcpState *st = p.st;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
+    // per-block partial sums: threads (fixed tree per sum) -> blocks (fixed order, by the last block to finish)
+    __syncthreads();
+    if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x + 3] = gtime();
+    for (int k = warp; k < kSums; k += kWarps) {
+        double v = 0;
+#pragma unroll
+        for (int t = 0; t < COLS / 32; ++t) v += s_acc[k][lane + 32 * t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) {
+            p.partials[(size_t)k * gridDim.x + blockIdx.x] = v;  // [sum][block]
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    reduce_and_step(p, gridDim.x, s_est, s_norm, tag);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The search kernel: one launch per Gauss-Newton iteration.
 // Light phase — one thread per query: home voxel, then neighbours nearest-bounding-box first with the prune bound
@@ -567,7 +578,7 @@ __device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s
 // Queries are dealt to warps in chunks of 32 consecutive points, chunk c to block c % grid, so every block sees a
 // cross-section of the scan and the expensive regions (sparse, far from the sensor) spread over all SMs.
 #define SAGE_STAMP(i) do { if (p.dbg && pass == 0 && warp == 0) { __syncwarp(); if (lane == 0) p.dbg[kDbg * blockIdx.x + (i)] = gtime(); } } while (0)
-template <bool COUNT, bool POOLED = false>
+template <bool COUNT>
 __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
     constexpr int kWarps = kNnThreads / 32;
     // per-thread running sums live in shared memory (s_acc[k][thread]) so that the search loop keeps its registers
@@ -659,108 +670,6 @@ __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
             if (COUNT) n_scanned += hcnt;
         }
         SAGE_STAMP(6);
-        if constexpr (POOLED) {
-            // EXPERIMENTAL (SAGE_POOLED=1; written at the end of round 1 from the schedule model in profiles/r01l_visit_schedule_model.md,
-            // not yet run on a GPU).  Neighbour visits of the warp's 32 queries are pooled: every round each still-open query
-            // nominates its nearest open boxes, floor(32 / open queries) of them, the 32 lanes take one (query, voxel) visit each,
-            // and every query merges the (min1, min2, arg) results of its own visits; bounds are re-tightened between rounds.
-            // A warp pays sum-of-visits / 32 rounds instead of the visits of its slowest lane, and nothing is deferred.
-            __shared__ uint16_t s_item[kWarps][32];
-            __shared__ float s_r1[kWarps][32], s_r2[kWarps][32];
-            __shared__ uint32_t s_ri[kWarps][32];
-            const unsigned FULL = 0xffffffffu;
-            float sxm = 0, sxp = 0, sym = 0, syp = 0, szm = 0, szp = 0;
-            bool open_query = valid && !odd;
-            if (open_query) {
-                if (COUNT) n_probes += 1;
-                axis_bounds(bx, kx, vs32, p.box_margin, p.smin32, sxm, sxp);
-                axis_bounds(by, ky, vs32, p.box_margin, p.smin32, sym, syp);
-                axis_bounds(bz, kz, vs32, p.box_margin, p.smin32, szm, szp);
-            }
-            auto box_lb = [&](int id) {
-                const int ox = id / 9, oy = (id / 3) % 3, oz = id % 3;
-                return (ox == 0 ? sxm : (ox == 2 ? sxp : 0.0f)) + (oy == 0 ? sym : (oy == 2 ? syp : 0.0f)) + (oz == 0 ? szm : (oz == 2 ? szp : 0.0f));
-            };
-            uint32_t visited = 1u << 13;
-#pragma unroll 1
-            while (true) {
-                uint32_t open = 0;
-                if (open_query && !odd) {
-                    const float bound = prune_bound(p, min1);
-#pragma unroll 1
-                    for (int id = 0; id < 27; ++id)
-                        if (!((visited >> id) & 1u) && box_lb(id) <= bound) open |= 1u << id;
-                }
-                const unsigned am = __ballot_sync(FULL, open != 0);
-                if (am == 0) break;
-                const int quota = max(1, 32 / __popc(am));
-                const int mine = min(quota, __popc(open));
-                int pre = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(FULL, pre, o);
-                    if (lane >= o) pre += t;
-                }
-                const int start = pre - mine, total = __shfl_sync(FULL, pre, 31);  // total <= open queries * quota <= 32
-                uint32_t left = open;
-#pragma unroll 1
-                for (int t = 0; t < mine; ++t) {  // nearest open box first
-                    float best_lb = INF;
-                    int nn = -1;
-                    for (uint32_t m = left; m; m &= m - 1) {
-                        const int id = __ffs(m) - 1;
-                        const float lb = box_lb(id);
-                        if (lb < best_lb) best_lb = lb, nn = id;
-                    }
-                    left &= ~(1u << nn);
-                    visited |= 1u << nn;
-                    s_item[warp][start + t] = (uint16_t)((lane << 8) | nn);
-                }
-                __syncwarp();
-                // lane j takes visit j: the owner's query through shuffles, the voxel from the item
-                const bool have = lane < total;
-                const uint32_t item = have ? s_item[warp][lane] : (uint32_t)(lane << 8);
-                const int ql = (int)(item >> 8), id = (int)(item & 0xffu);
-                const int qkx = __shfl_sync(FULL, kx, ql), qky = __shfl_sync(FULL, ky, ql), qkz = __shfl_sync(FULL, kz, ql);
-                const float qbx = __shfl_sync(FULL, bx, ql), qby = __shfl_sync(FULL, by, ql), qbz = __shfl_sync(FULL, bz, ql);
-                const float qql = __shfl_sync(FULL, qlf, ql);
-                float r1 = INF, r2 = INF;
-                uint32_t ri = kNil;
-                bool rodd = false;
-                if (have) {
-                    const int ox = id / 9 - 1, oy = (id / 3) % 3 - 1, oz = id % 3 - 1;
-                    const int nx = qkx + ox, ny = qky + oy, nz = qkz + oz;
-                    uint32_t nblk = 0, ncnt = 0;
-                    if (COUNT) n_probes += 1;
-                    if (key_in_range(nx, ny, nz) && tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), nblk, ncnt) && ncnt > 0) {
-                        scan_voxel_thread(p.blk_hot, nblk * (uint32_t)p.stride, ncnt, qbx - (float)ox * vs32, qby - (float)oy * vs32,
-                                          qbz - (float)oz * vs32, qql, th32, r1, r2, ri, rodd);
-                        if (COUNT) n_scanned += ncnt;
-                    }
-                }
-                s_r1[warp][lane] = r1, s_r2[warp][lane] = r2, s_ri[warp][lane] = ri;
-                const unsigned oddm = __ballot_sync(FULL, rodd);
-                __syncwarp();
-#pragma unroll 1
-                for (int t = 0; t < mine; ++t) {  // merge: (min1, min2, arg) of the union of two record sets; a tie keeps min2 == min1
-                    const int j = start + t;
-                    const float a1 = s_r1[warp][j], a2 = s_r2[warp][j];
-                    if (a1 < min1) {
-                        min2 = fminf(min1, a2), min1 = a1, idx1 = s_ri[warp][j];
-                    } else {
-                        min2 = fminf(min2, a1);
-                    }
-                    odd |= ((oddm >> j) & 1u) != 0;
-                }
-                __syncwarp();  // s_item / s_r* are rewritten by the next round
-            }
-            if (open_query && !odd && min1 < INF) {
-                if (min2 > band_limit(p, min1))
-                    widx = idx1;
-                else
-                    odd = true;
-            }
-        } else
         if (valid && !odd) {
             if (COUNT) n_probes += 1;
             // ---- neighbours, nearest bounding box first, while one can still beat the best so far ----
@@ -910,12 +819,6 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(IterParams p) {
     nn_search_iteration<COUNT>(p);
 }
-// EXPERIMENTAL, off unless SAGE_POOLED=1: the pooled neighbour schedule (see nn_search_iteration)
-template <bool COUNT>
-__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_pooled_kernel(IterParams p) {
-    nn_search_iteration<COUNT, true>(p);
-}
-
 // The whole Gauss-Newton loop of one registration in ONE cooperative launch: every block runs the iteration above, the grid
 // meets at a barrier (the last block has solved and updated IcpState by then), and the loop ends when `done` is set — no
 // launch gap, no host poll between iterations.  Used for the small scans of the pipeline level, where an iteration is ~20 us
@@ -966,7 +869,7 @@ void VoxelMapGPU::profile_enable(bool on) {
 }
 
 // launches = Gauss-Newton iterations timed (a persistent launch counts every iteration it ran), ms = their total device time
-void VoxelMapGPU::profile_read(long long *launches, double *ms) {
+void VoxelMapGPU::profile_read(long long *launches, double *ms, long long *kernel_launches) {
     set_device();
     SAGE_CUDA(cudaStreamSynchronize(stream_));
     double total = 0;
@@ -978,6 +881,7 @@ void VoxelMapGPU::profile_read(long long *launches, double *ms) {
         iters += prof_iters_[i];
     }
     if (launches) *launches = iters;
+    if (kernel_launches) *kernel_launches = (long long)prof_used_;
     if (ms) *ms = total;
     prof_used_ = 0;
 }
@@ -1000,6 +904,11 @@ void VoxelMapGPU::prof_end(int iterations) {
     ++prof_used_;
 }
 
+static const void *tile_kernel_ptr(int minb, bool persistent) {
+    if (persistent) return minb == 4 ? (const void *)nn_tile_persistent_kernel<4> : minb == 5 ? (const void *)nn_tile_persistent_kernel<5> : (const void *)nn_tile_persistent_kernel<6>;
+    return minb == 4 ? (const void *)nn_tile_kernel<4> : minb == 5 ? (const void *)nn_tile_kernel<5> : (const void *)nn_tile_kernel<6>;
+}
+
 static long env_long(const char *name, long dflt) {
     const char *e = getenv(name);
     return e ? atol(e) : dflt;
@@ -1012,7 +921,6 @@ void VoxelMapGPU::init_search_config() {
     SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nn_search_kernel<false>, kNnThreads, 0));
     nn_grid_ = sm_count_ * (per_sm > 0 ? per_sm : 1);
     if (const char *e = getenv("SAGE_LIGHT_PROBES")) light_probes_ = atoi(e);  // tuning knobs
-    pooled_ = env_long("SAGE_POOLED", 0) != 0;  // experimental schedule, see nn_search_iteration
     all_warp_max_ = (size_t)nn_grid_ * (kNnThreads / 32) * 3 / 4;
     all_warp_max_ = (size_t)env_long("SAGE_ALL_WARP_MAX", (long)all_warp_max_);
     if (getenv("SAGE_NO_ALL_WARP")) all_warp_max_ = 0;
@@ -1029,21 +937,17 @@ void VoxelMapGPU::init_search_config() {
     // tile search: staging area (dynamic shared memory) + co-resident grid
     static_assert(kTileThreads == 128, "tile_sort.cu cuts units of 128 queries");
     tile_stage_cap_ = (uint32_t)env_long("SAGE_TILE_STAGE", 1536);  // records of 16 bytes: 24 KB
-    tile_minb_ = env_long("SAGE_TILE_MINB", 6) <= 4 ? 4 : 6;
+    tile_minb_ = (int)env_long("SAGE_TILE_MINB", 5);  // which instantiation: resident blocks per SM the register allocation aims at
+    if (tile_minb_ < 4) tile_minb_ = 4;
+    if (tile_minb_ > 6) tile_minb_ = 6;
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
-    const void *k1 = tile_minb_ == 4 ? (const void *)nn_tile_kernel<4> : (const void *)nn_tile_kernel<6>;
-    const void *k2 = tile_minb_ == 4 ? (const void *)nn_tile_persistent_kernel<4> : (const void *)nn_tile_persistent_kernel<6>;
+    const void *k1 = tile_kernel_ptr(tile_minb_, false), *k2 = tile_kernel_ptr(tile_minb_, true);
     SAGE_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SAGE_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     SAGE_CUDA(cudaFuncSetAttribute(nn_tile_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm_t = 0, per_sm_tp = 0;
-    if (tile_minb_ == 4) {
-        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, nn_tile_kernel<4>, kTileThreads, smem));
-        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tp, nn_tile_persistent_kernel<4>, kTileThreads, smem));
-    } else {
-        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, nn_tile_kernel<6>, kTileThreads, smem));
-        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tp, nn_tile_persistent_kernel<6>, kTileThreads, smem));
-    }
+    SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k1, kTileThreads, smem));
+    SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tp, k2, kTileThreads, smem));
     int per_sm_tile = per_sm_t < per_sm_tp ? per_sm_t : per_sm_tp;
     const int want = (int)env_long("SAGE_TILE_BLOCKS", per_sm_tile);
     if (want >= 1 && want < per_sm_tile) per_sm_tile = want;
@@ -1051,7 +955,6 @@ void VoxelMapGPU::init_search_config() {
     tile_min_ = tile_grid_ > 0 ? (size_t)env_long("SAGE_TILE_MIN", 16384) : 0;
     if (tile_grid_ > 0 && tile_min_ < 1) tile_min_ = 1;
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
-    tile_probes_ = (int)env_long("SAGE_TILE_PROBES", 3);
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
     {
         const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
@@ -1091,6 +994,7 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
         for (int k = 0; k < peer_world_; ++k) p.xchg_peer[k] = peer_buf_[k];
     }
     p.tile_units = tile_units_.p, p.tile_n_units = tile_nunits_.p, p.tile_perm = tile_vals_[1].p, p.tile_stage_cap = tile_stage_cap_;
+    p.tile_unit_part = tile_unit_part_.p, p.tile_group_cnt = tile_group_cnt_.p;
 }
 
 // mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
@@ -1105,14 +1009,15 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         tile_prepare(src, n, pose_identity(), false);
         IterParams p;
         fill_params(p, src_.p, n, max_dist, kernel, sem_th, mode, tgt_out, matched_out);
-        p.light_probes = tile_probes_;
         const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
         if (mode == 2)
             SAGE_LAUNCH((nn_tile_kernel<4, true>), tile_grid_, kTileThreads, smem, stream_, p, 1);
-        else if (tile_minb_ == 4)
-            SAGE_LAUNCH(nn_tile_kernel<4>, tile_grid_, kTileThreads, smem, stream_, p, 1);
-        else
-            SAGE_LAUNCH(nn_tile_kernel<6>, tile_grid_, kTileThreads, smem, stream_, p, 1);
+        else {
+            int first = 1;
+            void *args[] = {&p, &first};
+            SAGE_CUDA(cudaLaunchKernel(tile_kernel_ptr(tile_minb_, false), dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
         return;
     }
     // chunks of 32 consecutive queries are dealt round-robin to the blocks; a full grid (a multiple of the SM count) once
@@ -1139,11 +1044,6 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         void *args[] = {&p, &persistent_iters};
         SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);
-    } else if (pooled_) {
-        if (mode == 2)
-            SAGE_LAUNCH(nn_search_pooled_kernel<true>, grid, kNnThreads, 0, stream_, p);
-        else
-            SAGE_LAUNCH(nn_search_pooled_kernel<false>, grid, kNnThreads, 0, stream_, p);
     } else if (mode == 2) {
         SAGE_LAUNCH(nn_search_kernel<true>, grid, kNnThreads, 0, stream_, p);
     } else {
@@ -1161,21 +1061,19 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
 void VoxelMapGPU::launch_tile(size_t n, double max_dist, double kernel, double sem_th, int iter_index, int persistent_iters) {
     IterParams p;
     fill_params(p, src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr);
-    p.light_probes = tile_probes_;
     p.dbg = dbg_on_ ? dbg_.p : nullptr;
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
     prof_begin();
     if (persistent_iters > 0) {
         void *args[] = {&p, &persistent_iters};
-        const void *k = tile_minb_ == 4 ? (const void *)nn_tile_persistent_kernel<4> : (const void *)nn_tile_persistent_kernel<6>;
-        SAGE_CUDA(cudaLaunchCooperativeKernel(k, dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
+        SAGE_CUDA(cudaLaunchCooperativeKernel(tile_kernel_ptr(tile_minb_, true), dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else {
         p.xchg_tag += (unsigned long long)iter_index;
-        if (tile_minb_ == 4)
-            SAGE_LAUNCH(nn_tile_kernel<4>, tile_grid_, kTileThreads, smem, stream_, p, iter_index == 0 ? 1 : 0);
-        else
-            SAGE_LAUNCH(nn_tile_kernel<6>, tile_grid_, kTileThreads, smem, stream_, p, iter_index == 0 ? 1 : 0);
+        int first = iter_index == 0 ? 1 : 0;
+        void *args[] = {&p, &first};
+        SAGE_CUDA(cudaLaunchKernel(tile_kernel_ptr(tile_minb_, false), dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
     }
     prof_end(1);
     if (comm_ != nullptr && peer_world_ <= 1) {

@@ -2,8 +2,9 @@
 // the ordered array into units for the tile search (search_tile.cuh).  The order is a locality hint only: the tile kernel
 // recomputes every unit's region from the queries' actual voxels each iteration, so a poor order costs time, never correctness.
 //
-//   tile_key_kernel     key = low 10 bits of each cell coordinate (cells repeat every 1024 cells = 1.6 km at 0.8 m voxels; two
-//                       aliasing cells in one run merely make a unit whose region does not fit, which falls back to global search)
+//   tile_key_kernel     key = low 9 bits of each cell coordinate + the voxel inside the cell (cells repeat every 512 cells = 819 m
+//                       at 0.8 m voxels; two aliasing cells in one run merely make a unit whose region does not fit, which falls
+//                       back to global search)
 //   cub::DeviceRadixSort::SortPairs over the 30 key bits (stable, deterministic: equal inputs give equal unit lists, which is
 //                       what makes the sums reproducible run to run)
 //   tile_gather_kernel  src[j] = guess * frame[perm[j]] (or a plain gather for the correspondence-only entry points) — TransformPoints(initial_guess, source), core/Registration.cpp:122-123 —
@@ -50,13 +51,16 @@ __global__ void tile_key_kernel(const double4 *__restrict__ frame, uint32_t n, P
     const double4 s = frame[i];
     double x = s.x, y = s.y, z = s.z;
     if (apply) pose_act(guess, s.x, s.y, s.z, x, y, z);
-    const int cx = trunc_div(x, vs) >> 1, cy = trunc_div(y, vs) >> 1, cz = trunc_div(z, vs) >> 1;  // arithmetic shift = floor
-    keys[i] = ((uint32_t)(cx & 1023) << 20) | ((uint32_t)(cy & 1023) << 10) | (uint32_t)(cz & 1023);
+    // cell = voxel >> 1 (arithmetic shift = floor), 9 bits per axis, then the voxel inside the cell: queries that share a home
+    // voxel are neighbours in the order, so a warp's home-bucket scan is converged
+    const int vx = trunc_div(x, vs), vy = trunc_div(y, vs), vz = trunc_div(z, vs);
+    keys[i] = ((uint32_t)((vx >> 1) & 511) << 21) | ((uint32_t)((vy >> 1) & 511) << 12) | ((uint32_t)((vz >> 1) & 511) << 3) |
+              ((uint32_t)(vx & 1) << 2) | ((uint32_t)(vy & 1) << 1) | (uint32_t)(vz & 1);
     vals[i] = i;
 }
 
 __device__ __forceinline__ bool unit_head(const uint32_t *__restrict__ keys, uint32_t j) {
-    return j == 0 || (j % kUnitQueries) == 0 || keys[j] != keys[j - 1];
+    return j == 0 || (j % kUnitQueries) == 0 || (keys[j] >> 3) != (keys[j - 1] >> 3);  // a new cell, or a full unit
 }
 
 __global__ void __launch_bounds__(256) tile_gather_kernel(const double4 *__restrict__ frame, uint32_t n, Pose guess, int apply,
@@ -134,6 +138,13 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
     const uint32_t tiles = (n32 + kHeadTile - 1) / kHeadTile;
     tile_heads_.ensure(tiles + 1);
     tile_nunits_.ensure(1);
+    // per-unit sums and per-group arrival counters of the two-level reduction (search_tile.cuh); the counters reset themselves at
+    // the end of every iteration, the memset only covers a registration that was abandoned half way (an error)
+    tile_unit_part_.ensure((n + 1) * 17);
+    const size_t groups = (n + 1) / 16 + 2;
+    tile_group_cnt_.ensure(groups);
+    SAGE_CUDA(cudaMemsetAsync(tile_group_cnt_.p, 0, groups * sizeof(uint32_t), stream_));
+    if ((size_t)17 * groups > partials_.cap) partials_.ensure((size_t)17 * groups);
     const size_t tmp_bytes = sort_pairs_tmp_bytes_u32(n, 30);
     tile_tmp_.ensure(tmp_bytes ? tmp_bytes : 1);
     SAGE_LAUNCH(tile_key_kernel, (n32 + 255) / 256, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, voxel_size_, tile_keys_[0].p,

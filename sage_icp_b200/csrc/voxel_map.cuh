@@ -104,7 +104,7 @@ public:
     int device() const { return device_; }
     size_t debug_timeline(unsigned long long *out, size_t cap);
     void profile_enable(bool on);
-    void profile_read(long long *launches, double *ms);
+    void profile_read(long long *iterations, double *ms, long long *kernel_launches = nullptr);
 
     void comm_init(int rank, int world, const uint8_t id[128]);
     void comm_destroy();
@@ -180,18 +180,18 @@ private:
     DevBuf<double> partials_;
     int nn_grid_ = 0;
     size_t all_warp_max_ = 0;  // scans up to this many queries use the warp-per-query mode
-    bool pooled_ = false;        // SAGE_POOLED=1: experimental pooled neighbour schedule of the search kernel
     int persistent_grid_ = 0;    // co-resident blocks of the persistent kernel
     size_t persistent_max_ = 0;  // scans up to this many queries run the whole GN loop in one cooperative launch
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
     // tile search
     DevBuf<uint32_t> tile_keys_[2], tile_vals_[2], tile_units_, tile_heads_, tile_nunits_;
     DevBuf<uint8_t> tile_tmp_;
+    DevBuf<double> tile_unit_part_;      // [unit][17] sums of one unit
+    DevBuf<uint32_t> tile_group_cnt_;    // units of a group that have published their sums
     int tile_grid_ = 0;            // co-resident blocks of the tile kernels
     int tile_minb_ = 6;            // which instantiation: 6 (80 registers) or 4 (128 registers) resident blocks per SM aimed at
     size_t tile_min_ = 0;          // scans of at least this many queries take the tile search (0 = never)
     uint32_t tile_stage_cap_ = 0;  // staging area of a block, in 16-byte records
-    int tile_probes_ = 3;          // occupied neighbour buckets a thread scans before its warp finishes the query
     bool tile_persistent_ = true;  // whole GN loop in one cooperative launch
     bool coop_ok_ = false;
     int light_probes_ = -1;  // < 0: chosen from the number of queries (launch_iteration); SAGE_LIGHT_PROBES overrides

@@ -37,7 +37,7 @@ def pytest_collection_modifyitems(config, items):
 SEARCH_MODES = {
     "default": {},                                                              # tile search from 16 384 queries up
     "tile": {"SAGE_TILE_MIN": "1"},                                             # tile search for every size, persistent loop
-    "tile_warp": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PROBES": "0", "SAGE_TILE_PERSISTENT": "0"},  # every neighbour by the warp phase
+    "tile_launch": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PERSISTENT": "0", "SAGE_TILE_MINB": "6"},  # one launch per iteration, 80 registers
     "tile_spill": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "96", "SAGE_TILE_MINB": "4"},       # staging area too small: global scans
     "legacy": {"SAGE_TILE": "0"},                                               # thread-per-query + deferred warp phase only
 }
@@ -45,7 +45,7 @@ SEARCH_MODES = {
 
 @pytest.fixture(params=list(SEARCH_MODES))
 def search_mode(request, monkeypatch):
-    for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_PROBES", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB"):
+    for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in SEARCH_MODES[request.param].items():
         monkeypatch.setenv(k, v)

@@ -14,7 +14,7 @@ BASIC_LABELS = [40, 44, 48, 49, 50, 70, 72]
 def _maps(orc, pts, monkeypatch=None, env=None):
     import sage_icp_b200 as sg
     if env is not None:
-        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_PROBES", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB"):
+        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -44,11 +44,11 @@ def _check_corr(g, o, q, max_dist, th):
     return int(matched.sum())
 
 
-@pytest.mark.parametrize("env", [{}, {"SAGE_TILE_PROBES": "0"}, {"SAGE_TILE_PROBES": "27"}, {"SAGE_TILE_STAGE": "128"}, {"SAGE_TILE_MINB": "4"}],
-                         ids=["default", "warp_phase_only", "thread_phase_only", "tiny_staging", "128_registers"])
+@pytest.mark.parametrize("env", [{}, {"SAGE_TILE_STAGE": "128"}, {"SAGE_TILE_MINB": "4"}, {"SAGE_TILE_MINB": "6", "SAGE_TILE_BLOCKS": "2"}],
+                         ids=["default", "tiny_staging", "128_registers", "80_registers_2_blocks_per_sm"])
 def test_tile_correspondences_bit_exact_on_a_full_scan(orc, monkeypatch, env):
     """32 000 queries of a street scan (above the 16 384-query threshold): every query's target equals the oracle's, in the
-    caller's order, for each way of splitting the work between the thread phase, the warp phase and global-memory scans."""
+    caller's order, whether the buckets fit the staging area or are scanned from global memory, for each register budget."""
     pts = _street()
     g = _maps(orc, pts, monkeypatch, env)
     o = orc.OracleMap(0.8, 1e9, 20, 20, BASIC_LABELS, evict_faithful=False)
@@ -60,8 +60,7 @@ def test_tile_correspondences_bit_exact_on_a_full_scan(orc, monkeypatch, env):
     assert _check_corr(g, o, q, 3.0, 0.4) > 20000
     scanned, probes, exact, heavy, staged = g.search_work(q, 3.0, 0.4, with_staged=True)
     assert staged > 0  # the buckets really went through the bulk copies
-    if env.get("SAGE_TILE_PROBES") == "0":
-        assert heavy > 0
+    assert heavy > 0   # ... and some (query, bucket) pairs through the pooled round
 
 
 def test_tile_registration_equals_legacy_and_is_reproducible(orc, monkeypatch):

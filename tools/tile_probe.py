@@ -8,16 +8,12 @@ import bench
 
 CONFIGS = {
     "legacy": {"SAGE_TILE": "0"},
-    "legacy_pooled": {"SAGE_TILE": "0", "SAGE_POOLED": "1"},
     "tile": {"SAGE_TILE_MIN": "1"},
     "tile_launch_per_iter": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PERSISTENT": "0"},
-    "tile_128regs": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "4"},
-    "tile_probes0": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PROBES": "0"},
-    "tile_probes1": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PROBES": "1"},
-    "tile_probes8": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PROBES": "8"},
-    "tile_probes27": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PROBES": "27"},
-    "tile_stage1024": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "1024"},
-    "tile_stage2560": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "2560"},
+    "tile_minb4": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "4"},
+    "tile_minb6_stage1024": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "6", "SAGE_TILE_STAGE": "1024"},
+    "tile_minb5_stage1024": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "5", "SAGE_TILE_STAGE": "1024"},
+    "tile_stage2048": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "2048"},
     "tile_blocks4": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "4"},
     "tile_blocks3": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "3"},
 }
@@ -50,7 +46,7 @@ for name in which:
                "pose": [float(f"{v:.12g}") for v in pose]}
         if n == sizes[-1]:
             w = m.search_work(sub, 3.0, 0.4, with_staged=True)
-            row["work_per_query"] = {"ranked": w[0] / len(sub), "probes": w[1] / len(sub), "exact": w[2] / len(sub), "warp_phase": w[3] / len(sub),
+            row["work_per_query"] = {"ranked": w[0] / len(sub), "probes": w[1] / len(sub), "exact": w[2] / len(sub), "pooled_pairs": w[3] / len(sub),
                                      "staged": w[4] / len(sub)}
         rows.append(row)
         print(json.dumps(row), flush=True)
@@ -77,8 +73,8 @@ if os.environ.get("TILE_TIMELINE", "1") != "0":
     b = buf[:K * g].reshape(g, K).astype(np.int64)
     b = b[b[:, 0] > 0]
     t0 = b[:, 0].min()
-    names = {1: "A load+transform+box", 2: "C probes+scan+issue", 3: "bulk wait", 4: "D thread phase", 5: "E warp phase", 6: "F/G fallback+exact",
-             7: "H accept+sums", 8: "end barrier"}
+    names = {8: "unit fetch", 1: "A load+transform+box", 2: "C probes+scan+issue", 3: "bulk wait", 4: "D rounds 0+1 (own thread)", 5: "E round 2 (pooled)",
+             6: "F/G fallback+exact", 7: "H accept+sums"}
     print(f"tile timeline: {len(b)} blocks, start spread {b[:,0].max()-t0} ns, block end (before finish) med {np.median(b[:,9]-t0):.0f} p90 "
           f"{np.percentile(b[:,9]-t0,90):.0f} max {(b[:,9]-t0).max()} ns; units/block med {np.median(b[:,10]):.1f} max {b[:,10].max()}, "
           f"queries/block med {np.median(b[:,11]):.0f} max {b[:,11].max()}")

@@ -11,8 +11,15 @@ voxel map, exactly 10 Gauss-Newton iterations (threshold 0 => no early exit).  O
   N > 1  : the scan's queries are sharded by index over the ranks (sage_shard_range), every rank holds a replica of
            the map, and the 17 normal-equation sums are all-reduced with NCCL every iteration  => "strong" scaling
 
---impl reference times the reference's CPU algorithm (the oracle port; the reference itself cannot be built here)
-on the host cores with OpenMP on the same workload.
+--impl reference times the reference's CPU algorithm on ALL host cores (os.sched_getaffinity, whatever OMP_NUM_THREADS a
+launcher set) on the same workload, every query of every scan: the oracle port (OpenMP) and, where its build travelled, the
+reference's own sources compiled against stand-in third-party headers (oracle/_ref); the line's value is the faster of the two.
+
+Extra objects of the main line (N = 1): `pipeline` = BASELINE configs[0], the function the north star names — one 120 k-point
+scan through sage_register_frame (pageable host buffer) against a pre-built 1 M-point map, next to the CPU port single-threaded
+("TBB off") and on all cores, pose delta; `roofline_hbm_regime` = the same kernel on queries spread uniformly over a 50 M-point
+map (no reuse between queries: the DRAM-bound regime).  N > 1: `sharded_pose_delta_m` = |pose of the sharded run - pose of the
+unsharded run on rank 0's GPU| (asserted <= 1e-10).
 """
 from __future__ import annotations
 
@@ -143,6 +150,14 @@ def emit(text: str):
     out.flush()
 
 
+def host_cores() -> int:
+    """Cores this process may run on — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -184,8 +199,9 @@ def run_reference(args):
     cpu_baseline names it and carries both."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    threads = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # before libgomp initialises (the library is loaded below); the calls also pass it
     from oracle import oracle_py as orc
-    threads = orc.max_threads()
     half = street_half_length(args.map_points)
     map_pts = make_map_points(args.map_points)
     omap = orc.OracleMap(VOXEL_SIZE_MAP, 1e9, BASIC, CRITICAL, BASIC_LABELS)
@@ -209,10 +225,13 @@ def run_reference(args):
     kind = "reference" if ms_rb is not None and ms_rb < ms_port else "port"
     ms = ms_rb if kind == "reference" else ms_port
     v = 1e3 / ms
-    sample = (f"{args.steps} scans, every {max(1, int(round(1 / frac)))}-th query of each 120k-pt scan x {ITERS} GN iters, time scaled to the "
-              f"full scan; value = the faster of: oracle port (OpenMP) {1e3 / ms_port:.2f} scans/s"
-              + (f", reference's own code (oracle/_ref, stand-in third-party headers, runs of {int(np.mean(iters_rb))} iterations scaled to "
-                 f"{ITERS}) {1e3 / ms_rb:.2f} scans/s" if ms_rb is not None else ", reference build not present"))
+    stride = max(1, int(round(1 / frac)))
+    sample = (f"{args.steps} scans, " + ("every query" if stride == 1 else f"every {stride}-th query (time scaled to the full scan)")
+              + f" of each {args.beams * args.az // 1000}k-pt scan x {ITERS} GN iters on {threads} host threads; value = the faster of: oracle "
+              f"port (OpenMP) {1e3 / ms_port:.2f} scans/s"
+              + (f", reference's own sources compiled against STAND-IN Eigen/Sophus/oneTBB/tsl headers (oracle/_ref; its parallel_reduce "
+                 f"stand-in is a plain chunked thread pool, not TBB; runs of {int(np.mean(iters_rb))} iterations scaled to {ITERS}) "
+                 f"{1e3 / ms_rb:.2f} scans/s" if ms_rb is not None else ", reference build not present"))
     emit(json.dumps({
         "impl": "reference", "metric": "RegisterFrame scans/sec (120 k-pt labeled scan)", "value": v, "unit": "scans/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -236,6 +255,116 @@ def workload_config(args, map_points, map_voxels):
                             + ("fused into the search kernel over NVLink peer memory" if args.comm == "peer" else "by NCCL")) if args.gpus > 1 else "single GPU"}
 
 
+def transform_by_guess(q: np.ndarray, g: np.ndarray) -> np.ndarray:
+    """Positions the first Gauss-Newton iteration sees (yaw-only guess applied), for the occupancy statistics."""
+    yaw = 2.0 * math.atan2(g[5], g[6])
+    c, sn = math.cos(yaw), math.sin(yaw)
+    qq = q.copy()
+    qq[:, 0] = c * q[:, 0] - sn * q[:, 1] + g[0]
+    qq[:, 1] = sn * q[:, 0] + c * q[:, 1] + g[1]
+    qq[:, 2] = q[:, 2] + g[2]
+    return qq
+
+
+def pipeline_leg(sg, device: int, reps: int = 8):
+    """BASELINE configs[0] at pipeline level: ONE 120 k-point labelled scan through sage_register_frame — the C-ABI call behind
+    sageICP::RegisterFrame(frame): Preprocess + Voxelize + AdaptiveThreshold + ICP + map Update — from a PAGEABLE host buffer,
+    against a map pre-built from 1 M surface samples, next to the oracle port of the same function single-threaded ("TBB off")
+    and on all host cores; poses compared."""
+    from oracle import oracle_py as orc
+    from sage_icp_b200 import synthetic as syn
+    cfg = sg.launch_config()
+    world = make_map_points(1_000_000)
+    local = world.copy()
+    local[:, 2] -= syn.SENSOR_HEIGHT  # the pipeline's map frame is the first sensor frame: sensor at the origin
+    truth = (0.3, 0.1, math.radians(1.0))
+    scan = np.ascontiguousarray(syn.make_scan(4242, truth))  # plain numpy memory: pageable
+    gp = sg.SagePipeline(cfg, device=device) if "device" in sg.SagePipeline.__init__.__code__.co_varnames else sg.SagePipeline(cfg)
+    ms, pose_g = [], None
+    for r in range(reps + 2):
+        gp.reset()
+        gp.map().add_points(local)
+        n_map = gp.map().num_points()
+        t = time.perf_counter()
+        pose_g, _, _ = gp.register_frame(scan)
+        dt = time.perf_counter() - t
+        if r >= 2:
+            ms.append(1e3 * dt)
+    n_src, iters = len(gp.last_source()), gp.last_iterations()
+    out = {"workload": "BASELINE configs[0]: one 120k-pt labelled scan through sage_register_frame (sageICP::RegisterFrame: Preprocess, Voxelize, "
+                       "AdaptiveThreshold, ICP, map Update) from a pageable host buffer vs a map pre-built from 1 M samples, first frame "
+                       "(identity initial guess, sigma = initial_threshold)",
+           "scan_points": int(len(scan)), "map_points": int(n_map), "icp_queries_after_voxelize": int(n_src), "gn_iterations": int(iters),
+           "gpu_ms_per_frame": float(np.median(ms)), "gpu_frames_per_s": 1e3 / float(np.median(ms)), "timing": f"wall clock around the call, median of {reps}"}
+    cores = host_cores()
+    for name, threads in (("cpu_single_thread", 1), ("cpu_all_cores", cores)):
+        op = orc.OraclePipeline(cfg, threads=threads, evict_faithful=False)
+        best, pose_c = None, None
+        for r in range(2 if threads == 1 else 3):
+            op.reset()
+            op.map().add_points(local)
+            t = time.perf_counter()
+            pose_c, _, _ = op.register_frame(scan)
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+        out[name] = {"ms_per_frame": 1e3 * best, "frames_per_s": 1.0 / best, "threads": threads, "kind": "port",
+                     "iterations": op.last_iterations(), "queries": int(len(op.last_source()))}
+        out["pose_delta_vs_cpu_m"] = float(np.linalg.norm(pose_g[:3] - pose_c[:3]))
+        out["pose_delta_vs_cpu_rad"] = float(2.0 * min(np.linalg.norm(pose_g[3:] - pose_c[3:]), np.linalg.norm(pose_g[3:] + pose_c[3:])))
+    out["speedup_vs_single_thread"] = out["cpu_single_thread"]["ms_per_frame"] / out["gpu_ms_per_frame"]
+    out["speedup_vs_all_cores"] = out["cpu_all_cores"]["ms_per_frame"] / out["gpu_ms_per_frame"]
+    return out
+
+
+def hbm_regime_leg(sg, torch, device: int, map_points: int, base_pts: np.ndarray, base_half: float, peak: float, reps: int = 6):
+    """BASELINE configs[4]'s DRAM-bound end: 120 k queries spread uniformly over a `map_points`-point map (no two queries share
+    a bucket, nothing stays L2-resident), same kernel, 10 GN iterations.  The map is the bench map tiled along the street."""
+    rng = np.random.default_rng(7)
+    m = sg.SageMap(VOXEL_SIZE_MAP, 1e9, BASIC, CRITICAL, BASIC_LABELS, device=device)
+    tiles = max(1, int(round(map_points / 5_000_000)))
+    period = 2.0 * base_half + 40.0
+    uq = []
+    for t in range(tiles):
+        pts = base_pts.copy()
+        pts[:, 0] += t * period
+        m.add_points(pts)
+        uq.append(pts[rng.choice(len(pts), 120_000 // tiles + 1, replace=False)])
+    q = np.concatenate(uq)[:120_000].copy()
+    q[:, :3] += rng.normal(0, 0.1, (len(q), 3))  # near, not on, map points
+    q = np.ascontiguousarray(q[rng.permutation(len(q))])
+    ident = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    occ, cand = m.nn_stats(q)
+    alg = algorithmic_bytes(len(q), occ, cand)
+    work = m.search_work(q, MAX_DIST, SEM_TH, with_staged=True)
+    d = torch.from_numpy(q).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(2):
+        m.register_frame_device(d.data_ptr(), len(q), ident, MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
+    m.profile_enable(True)
+    for _ in range(reps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        m.register_frame_device(d.data_ptr(), len(q), ident, MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
+    iters, launches, ms = m.profile_read_launches()
+    m.profile_enable(False)
+    us = 1e3 * ms / max(1, iters)
+    requested = 16.0 * (work[4] + work[1]) + 96.0 * len(q)  # staged records + table probes + query in/out + winner record
+    out = {"workload": f"120k queries uniform over a {m.num_points()}-pt / {m.num_voxels()}-voxel map ({tiles} copies of the bench map along x), "
+                       f"{ITERS} GN iterations, L2 flushed between registrations",
+           "bound": "hbm", "algorithmic_bytes_per_iteration": alg, "us_per_iteration": us, "achieved": alg / us / 1e3, "peak": peak,
+           "unit": "GB/s", "frac": alg / us / 1e3 / peak, "iterations_timed": int(iters), "launches_timed": int(launches),
+           "requested_bytes_per_iteration": requested, "requested_gbs": requested / us / 1e3,
+           "occupied_voxels_per_query": occ / len(q), "candidates_per_query": cand / len(q),
+           "traffic": None, "traffic_source": None}
+    tp = os.path.join(ROOT, "profiles", "traffic_hbm_regime.json")  # dram bytes per iteration from an ncu capture of this leg
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        out["traffic"], out["traffic_source"] = tj.get("dram_bytes_per_iteration"), tj.get("source")
+    del m, d, flush
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner under torchrun) is sent to
     # stderr instead, and the line itself goes to the saved descriptor
@@ -252,7 +381,10 @@ def main():
     ap.add_argument("--map-points", type=int, default=5_000_000)
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--az", type=int, default=1875)
-    ap.add_argument("--cpu-fraction", type=float, default=0.1, help="fraction of each scan the CPU arm times")
+    ap.add_argument("--cpu-fraction", type=float, default=1.0, help="fraction of each scan the CPU arm times (1.0 = every query)")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the configs[0] pipeline-level object")
+    ap.add_argument("--no-hbm-regime", action="store_true", help="skip the 50 M-point uniform-query roofline object")
+    ap.add_argument("--hbm-map-points", type=int, default=50_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N > 1: all-reduce of the normal equations fused into the search kernel over NVLink peer memory, or NCCL")
@@ -371,54 +503,69 @@ def main():
         flush.fill_(1)
         torch.cuda.synchronize()
         step_resident(s)
-    n_kernels, kernel_ms = gmap.profile_read()
+    n_iters, n_kernels, kernel_ms = gmap.profile_read_launches()
     gmap.profile_enable(False)
-    alg, work = [], np.zeros(4)
+    alg, work = [], np.zeros(5)
     for s in range(args.warmup, total):
-        q = shards_dev[s].cpu().numpy().copy()
         # statistics at the positions the first iteration sees (guess applied), counted exactly on the device map
-        qq = q.copy()
-        g = guesses[s]
-        yaw = 2.0 * math.atan2(g[5], g[6])
-        c, sn = math.cos(yaw), math.sin(yaw)
-        qq[:, 0] = c * q[:, 0] - sn * q[:, 1] + g[0]
-        qq[:, 1] = sn * q[:, 0] + c * q[:, 1] + g[1]
-        qq[:, 2] = q[:, 2] + g[2]
+        qq = transform_by_guess(shards_dev[s].cpu().numpy(), guesses[s])
         occ, cand = gmap.nn_stats(qq)
         alg.append(algorithmic_bytes(len(qq), occ, cand))
         if s < args.warmup + 4:  # what the kernel really touches (first-iteration positions), a few steps are enough
-            work += np.array(gmap.search_work(qq, MAX_DIST, SEM_TH)) / len(qq)
+            work += np.array(gmap.search_work(qq, MAX_DIST, SEM_TH, with_staged=True)) / len(qq)
             n_work = s - args.warmup + 1
-    bytes_per_launch = float(np.mean(alg))
+    bytes_per_iter = float(np.mean(alg))
+    iters_per_launch = n_iters / max(1, n_kernels)
     peak, peak_src = measured_peak_gbs()
-    achieved = bytes_per_launch * n_kernels / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+    achieved = bytes_per_iter * n_iters / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes/launch of the same kernel from an ncu --set full capture
     if os.path.exists(tp):
         tj = json.load(open(tp))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
 
+    # ---- N > 1: the sharded registration must give the unsharded pose (rank 0 repeats it alone on its own GPU) ----------
+    sharded_delta = None
+    if world > 1:
+        s = args.warmup
+        pose_sh, _ = gmap.register_frame_device(shards_dev[s].data_ptr(), shards_dev[s].shape[0], guesses[s], MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
+        if rank == 0:
+            solo = sg.SageMap(VOXEL_SIZE_MAP, 1e9, BASIC, CRITICAL, BASIC_LABELS, device=local)
+            solo.add_points(map_pts)
+            pose_1, _ = solo.register_frame(scans[s], guesses[s], MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
+            sharded_delta = float(np.linalg.norm(np.asarray(pose_sh) - np.asarray(pose_1)))
+            del solo
+            assert sharded_delta <= 1e-10, f"sharded pose differs from the unsharded one by {sharded_delta}"
+        barrier()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline (oracle port), bounded sample --------------------------------------------------------
+    # ---- CPU baseline on this box's host cores: the same scans, every query, all cores ---------------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle import oracle_py as orc
-        threads = orc.max_threads()
+        threads = host_cores()
         omap = orc.OracleMap(VOXEL_SIZE_MAP, 1e9, BASIC, CRITICAL, BASIC_LABELS)
         omap.add_points(map_pts)
         stride = max(1, int(round(1 / args.cpu_fraction)))
+        n_cpu = min(args.steps, 8)
+        t_all, pose_c = [], None
+        for k in range(n_cpu):
+            sub = scans[args.warmup + k][::stride]
+            t = time.perf_counter()
+            pose_k, _ = omap.register_frame_core(sub, guesses[args.warmup + k], MAX_DIST, KERNEL, SEM_TH, threads=threads, max_iters=ITERS, est_th=0.0)
+            t_all.append((time.perf_counter() - t) * len(scans[args.warmup + k]) / len(sub))
+            pose_c = pose_k if k == 0 else pose_c
+        t_all = float(np.mean(t_all))
         scan, guess = scans[args.warmup], guesses[args.warmup]
         sub = scan[::stride]
-        t = time.perf_counter(); pose_c, _ = omap.register_frame_core(sub, guess, MAX_DIST, KERNEL, SEM_TH, threads=threads, max_iters=ITERS, est_th=0.0)
-        t_all = (time.perf_counter() - t) * len(scan) / len(sub)
-        sub1 = scan[:: stride * 4]
+        sub1 = scan[::4]  # single thread ("TBB off"): a quarter of one scan, scaled
         t = time.perf_counter(); omap.register_frame_core(sub1, guess, MAX_DIST, KERNEL, SEM_TH, threads=1, max_iters=ITERS, est_th=0.0)
         t_one = (time.perf_counter() - t) * len(scan) / len(sub1)
-        # parity spot check on the sample (same sub-scan through the GPU path)
+        # parity check on the same scan through the GPU path
         pose_g, _ = gmap.register_frame(sub, guess, MAX_DIST, KERNEL, SEM_TH, ITERS, 0.0)
         try:  # the reference's own code, where its build travelled (extra information: never allowed to take the line down)
             t_rb, it_rb = ReferenceBuild(map_pts, threads).seconds_per_scan(omap, sub, guess, len(scan), threads)
@@ -426,16 +573,38 @@ def main():
             print(f"reference build not timed: {e}", file=sys.stderr)
             t_rb, it_rb = None, 0
         kind = "reference" if t_rb is not None and t_rb < t_all else "port"
-        sample = f"1 scan, every {stride}-th query x {ITERS} GN iters on the same {n_map_points}-pt map, time scaled to 120k queries"
+        sample = (f"{n_cpu} scans of the timed set, " + ("every query" if stride == 1 else f"every {stride}-th query, time scaled")
+                  + f", x {ITERS} GN iters on the same {n_map_points}-pt map, {threads} host threads (mean); single_thread_value: a quarter of one scan, scaled")
         if t_rb is not None:
-            sample += ("; value = the faster of the oracle port (OpenMP) and the reference's own code built against stand-in third-party "
-                       f"headers (oracle/_ref; a run of {it_rb} iterations scaled to {ITERS})")
+            sample += ("; value = the faster of the oracle port (OpenMP) and the reference's own sources compiled against STAND-IN "
+                       f"Eigen/Sophus/oneTBB/tsl headers (oracle/_ref: one scan, a run of {it_rb} iterations scaled to {ITERS}; its parallel_reduce "
+                       "stand-in is a plain chunked thread pool, not TBB)")
         cpu = {"value": 1.0 / (t_rb if kind == "reference" else t_all), "unit": "scans/s", "cores": threads, "kind": kind, "sample": sample,
                "port_value": 1.0 / t_all, "reference_build_value": (1.0 / t_rb) if t_rb is not None else None,
                "single_thread_value": 1.0 / t_one,
                "pose_delta_vs_gpu_m": float(np.linalg.norm(pose_g[:3] - pose_c[:3]))}
 
+    # ---- pipeline level (configs[0]) and the DRAM-bound regime (configs[4]) -------------------------------------------
+    pipeline = hbm = None
+    if world == 1 and not args.no_pipeline:
+        try:
+            pipeline = pipeline_leg(sg, local)
+        except Exception as e:  # noqa: BLE001 — an extra object must never take the line down
+            pipeline = {"error": f"{type(e).__name__}: {e}"}
+    if world == 1 and not args.no_hbm_regime and args.beams * args.az == 120000:
+        try:
+            del shards_dev, flush
+            torch.cuda.empty_cache()
+            hbm = hbm_regime_leg(sg, torch, local, args.hbm_map_points, map_pts, half, peak)
+        except Exception as e:  # noqa: BLE001
+            hbm = {"error": f"{type(e).__name__}: {e}"}
+
     n_scans = args.steps
+    tile = work[4] > 0
+    kernel_name = ("nn_tile_persistent_kernel" if tile and iters_per_launch > 1.5 else "nn_tile_kernel" if tile else "nn_search_kernel") + (
+        " (correspondence search over TMA-staged buckets + normal equations + GN step; " if tile else
+        " (correspondence search + normal equations + GN step; ") + (
+        f"one cooperative launch runs the {iters_per_launch:.0f} iterations of a registration)" if iters_per_launch > 1.5 else "1 launch per iteration)")
     line = {
         "metric": "RegisterFrame scans/sec (120 k-pt labeled scan)", "value": n_scans / (tot_ms * 1e-3), "unit": "scans/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms / args.steps,
@@ -445,17 +614,27 @@ def main():
                 "d2h_bytes_per_step": 7 * 8 + 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "nn_search_kernel (correspondence search + normal equations + GN step, 1 launch per iteration)",
+        "roofline": {"bound": "hbm", "kernel": kernel_name,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch, "launches_timed": int(n_kernels),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_iter * iters_per_launch, "launches_timed": int(n_kernels),
                      "avg_launch_us": 1e3 * kernel_ms / max(1, n_kernels),
+                     "gn_iterations_per_launch": iters_per_launch, "algorithmic_bytes_per_iteration": bytes_per_iter,
+                     "us_per_iteration": 1e3 * kernel_ms / max(1, n_iters),
                      "note": "achieved = algorithmic bytes of the reference's 27-voxel scan (SURVEY.md 8d) / measured kernel time; the kernel "
-                             "prunes voxels that provably cannot hold the arg-min, so it requests fewer bytes than that (kernel_work)",
-                     "kernel_work_per_query": {"records_scanned": work[0] / n_work, "table_probes": work[1] / n_work,
-                                               "f64_reranked": work[2] / n_work, "deferred_to_warp_phase": work[3] / n_work,
-                                               "requested_bytes": 16 * (work[0] + work[1]) / n_work + 32 + 32 + 32}},
+                             "prunes voxels that provably cannot hold the arg-min and shares staged buckets between the queries of a unit, so "
+                             "it requests far fewer bytes than that (kernel_work_per_query); on this L2-resident working set the figure is an "
+                             "algorithmic-throughput equivalence, not DRAM use — roofline_hbm_regime is the DRAM-bound measurement",
+                     "kernel_work_per_query": {"records_ranked": work[0] / n_work, "table_probes": work[1] / n_work,
+                                               "f64_reranked": work[2] / n_work,
+                                               ("pooled_pairs" if tile else "deferred_to_warp_phase"): work[3] / n_work,
+                                               "records_staged_by_tma": work[4] / n_work,
+                                               "requested_bytes": (16 * (work[4] + work[1]) if tile else 16 * (work[0] + work[1])) / n_work + 32 + 32 + 32}},
         "cpu_baseline": cpu,
+        "pipeline": pipeline,
+        "roofline_hbm_regime": hbm,
     }
+    if sharded_delta is not None:
+        line["sharded_pose_delta_m"] = sharded_delta
     emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

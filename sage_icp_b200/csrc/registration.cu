@@ -114,8 +114,8 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ double shfl_d(unsigned mask, double v, int lane) { return __shfl_sync(mask, v, lane); }
 
 // One Gauss-Newton step from the reduced sums: x = LDLT(JTJ)^-1 (-JTr); est = exp(x); T_icp = est * T_icp; stop when
-// |log(est)| < threshold (core/Registration.cpp:92-93,133-137).  Called by EVERY thread of a block of >= 64 threads (it
-// synchronises): thread 0 solves and exponentiates, then thread 0 (pose products) and thread 32 (log norm) run side by side.
+// |log(est)| < threshold (core/Registration.cpp:92-93,133-137).  icp_step_block is called by EVERY thread of a block of >= 64
+// threads (it synchronises).
 __device__ __noinline__ void icp_solve_xi(const double *S, double xi[6]) {
     // Normal equations with s = sum w s, r_t = sum w r, r_r = sum w (s x r):
     //   JTJ = [[ w I, -[s]x ], [ [s]x, C ]],  C = sum w (|s|^2 I - s s^T),   JTJ (u, o) = -(r_t, r_r).
@@ -159,21 +159,60 @@ __device__ __forceinline__ Pose load_pose_cg(const Pose *q) {
     const double *d = reinterpret_cast<const double *>(q);
     return Pose{__ldcg(d), __ldcg(d + 1), __ldcg(d + 2), __ldcg(d + 3), __ldcg(d + 4), __ldcg(d + 5), __ldcg(d + 6)};
 }
+// The step is a chain of dependent f64 operations (two divisions, sqrt, sin/cos, atan2: ~8 us in one thread), so the independent
+// pieces run side by side in two warps: [solve] -> [rotation part of exp | translation part of exp] -> [pose product | log norm]
+// -> [stop test; the final pose only when the loop ends].  Same formulas, same operation order as pose_exp / pose_log.
 __device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
+    __shared__ double s_xi[6];
     if (threadIdx.x == 0) {
         double xi[6];
         icp_solve_xi(st->sums, xi);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s_xi[i] = xi[i];
         if (dbg) dbg[5] = gtime();
-        *s_pose = pose_exp(xi);
-        if (dbg) dbg[6] = gtime();
     }
     __syncthreads();
+    if (threadIdx.x == 0 || threadIdx.x == 32) {  // Sophus SE3::exp, tangent = (upsilon, omega) — se3.cuh pose_exp, split in two
+        const double eps = 1e-10;
+        const double wx = s_xi[3], wy = s_xi[4], wz = s_xi[5];
+        const double th2 = (wx * wx + wy * wy) + wz * wz;
+        if (threadIdx.x == 0) {
+            double imag, real;
+            if (th2 < eps * eps) {
+                const double th4 = th2 * th2;
+                imag = 0.5 - (1.0 / 48.0) * th2 + (1.0 / 3840.0) * th4;
+                real = 1.0 - (1.0 / 8.0) * th2 + (1.0 / 384.0) * th4;
+            } else {
+                const double theta = sqrt(th2), half = 0.5 * theta;
+                imag = sin(half) / theta;
+                real = cos(half);
+            }
+            double qw = real, qx = imag * wx, qy = imag * wy, qz = imag * wz;
+            const double n = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
+            s_pose->qw = qw / n, s_pose->qx = qx / n, s_pose->qy = qy / n, s_pose->qz = qz / n;
+        } else {
+            const double theta = th2 < eps * eps ? 0.0 : sqrt(th2);
+            double a, b;
+            if (theta < eps) {
+                a = 0.5, b = 1.0 / 6.0;
+            } else {
+                a = (1.0 - cos(theta)) / th2;
+                b = (theta - sin(theta)) / (th2 * theta);
+            }
+            const double ux = s_xi[0], uy = s_xi[1], uz = s_xi[2];
+            const double c1x = wy * uz - wz * uy, c1y = wz * ux - wx * uz, c1z = wx * uy - wy * ux;
+            const double c2x = wy * c1z - wz * c1y, c2y = wz * c1x - wx * c1z, c2z = wx * c1y - wy * c1x;
+            s_pose->tx = ux + a * c1x + b * c2x;
+            s_pose->ty = uy + a * c1y + b * c2y;
+            s_pose->tz = uz + a * c1z + b * c2z;
+        }
+    }
+    __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[6] = gtime();
     if (threadIdx.x == 0) {
         const Pose est = *s_pose;
         st->est = est;
-        const Pose T = pose_mul(est, load_pose_cg(&st->T_icp));
-        st->T_icp = T;
-        st->result = pose_mul(T, st->guess);  // only read once done
+        st->T_icp = pose_mul(est, load_pose_cg(&st->T_icp));
         st->iter = __ldcg(&st->iter) + 1;
     } else if (threadIdx.x == 32) {
         double lg[6];
@@ -186,7 +225,10 @@ __device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, doubl
     __syncthreads();
     if (threadIdx.x == 0) {
         st->last_norm = *s_norm;
-        if (*s_norm < st->est_th || __ldcg(&st->iter) >= st->max_iters) st->done = 1;
+        if (*s_norm < st->est_th || st->iter >= st->max_iters) {
+            st->result = pose_mul(st->T_icp, st->guess);  // T_icp * guess (core/Registration.cpp:140): needed once, when the loop ends
+            st->done = 1;
+        }
     }
 }
 

@@ -168,13 +168,13 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     } while (0)
     unsigned long long n_ranked = 0, n_probes = 0, n_exact = 0, n_pooled = 0, n_staged = 0;  // work counters (COUNT launches only)
 
+    uint32_t next_unit = 0;  // thread 0: the unit after the current one, fetched while the current one is being worked on
+    if (threadIdx.x == 0) sh.unit = atomicAdd(&st->unit_next, 1u) - fetch_base;
     for (;;) {
-        __syncthreads();  // the previous unit is done with the shared state
-        if (threadIdx.x == 0) sh.unit = atomicAdd(&st->unit_next, 1u) - fetch_base;
-        for (int k = threadIdx.x; k < kSums * kTileCols; k += kTileThreads) (&sh.acc[0][0])[k] = 0.0;
-        __syncthreads();
+        __syncthreads();  // the previous unit is done with the shared state; sh.unit is set
         const uint32_t u = sh.unit;
         if (u >= n_units) break;
+        if (threadIdx.x == 0) next_unit = atomicAdd(&st->unit_next, 1u) - fetch_base;  // its latency hides behind phase A
         TILE_STAMP(8);
         const uint32_t ubeg = p.tile_units[u], uend = p.tile_units[u + 1];  // at most kTileThreads queries by construction
         const uint32_t q = ubeg + threadIdx.x;
@@ -426,10 +426,11 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
         }
         TILE_STAMP(6);
         // ---- H: acceptance on the exact records, residual, weight, the 16 sums + pair count -----------------------------------------
-        if (p.tgt_out != nullptr || __any_sync(FULL, widx != kNil)) {
+        {
             double a[kSums];
 #pragma unroll
             for (int k = 0; k < kSums; ++k) a[k] = 0.0;
+            const bool any_pair = __any_sync(FULL, widx != kNil);
             double4 nb = make_double4(0, 0, 0, 0);
             bool ok = false;
             if (widx != kNil) {
@@ -454,12 +455,14 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                 st256(p.tgt_out + dst, nb);
                 p.matched_out[dst] = ok ? 1 : 0;
             }
+            if (any_pair) {
 #pragma unroll
-            for (int k = 0; k < kSums; ++k) {
-                a[k] += __shfl_xor_sync(FULL, a[k], 1);
-                a[k] += __shfl_xor_sync(FULL, a[k], 2);
+                for (int k = 0; k < kSums; ++k) {
+                    a[k] += __shfl_xor_sync(FULL, a[k], 1);
+                    a[k] += __shfl_xor_sync(FULL, a[k], 2);
+                }
             }
-            if ((lane & 3) == 0) {
+            if ((lane & 3) == 0) {  // every column is written for every unit (zeros from a warp without pairs)
 #pragma unroll
                 for (int k = 0; k < kSums; ++k) sh.acc[k][threadIdx.x >> 2] = a[k];
             }
@@ -496,6 +499,7 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
             if (sh.flag == 2) reduce_and_step(p, n_groups, sh.est, sh.norm, tag);
         }
         if (p.dbg && threadIdx.x == 0) sh.dbg_t[10] += 1, sh.dbg_t[11] += uend - ubeg;
+        if (threadIdx.x == 0) sh.unit = next_unit;
     }
     if (p.dbg && threadIdx.x == 0) {
         sh.dbg_t[9] = gtime();

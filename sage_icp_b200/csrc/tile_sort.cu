@@ -8,7 +8,8 @@
 //   cub::DeviceRadixSort::SortPairs over the 30 key bits (stable, deterministic: equal inputs give equal unit lists, which is
 //                       what makes the sums reproducible run to run)
 //   tile_gather_kernel  src[j] = guess * frame[perm[j]] (or a plain gather for the correspondence-only entry points) — TransformPoints(initial_guess, source), core/Registration.cpp:122-123 —
-//                       and the per-tile count of unit heads (a new cell, or every kTileThreads-th position)
+//   tile_heads_kernel   unit boundaries: aligned chunks of 128 positions, cut where the next cell would not fit the unit's region
+//                       (gather also counts the heads per 1024-position tile)
 //   tile_units_kernel   compaction of the heads into units[0..n_units], units[n_units] = n
 #include <cub/device/device_radix_sort.cuh>
 
@@ -59,12 +60,40 @@ __global__ void tile_key_kernel(const double4 *__restrict__ frame, uint32_t n, P
     vals[i] = i;
 }
 
-__device__ __forceinline__ bool unit_head(const uint32_t *__restrict__ keys, uint32_t j) {
-    return j == 0 || (j % kUnitQueries) == 0 || (keys[j] >> 3) != (keys[j - 1] >> 3);  // a new cell, or a full unit
+// Unit boundaries.  One thread walks one aligned chunk of kUnitQueries sorted positions: a unit starts at the chunk start and
+// wherever taking in the next cell would make the unit's region — the bounding box of its cells, in voxels, grown by one voxel
+// on every side — larger than kMergeSlots.  Dense chunks (one to three cells) stay one full unit; sparse ones (a cell every few
+// queries) are cut where their cells stop being neighbours.  kMergeSlots leaves room for the queries to drift by a voxel per axis
+// during the Gauss-Newton iterations before a region outgrows the tile kernel's table (kTileSlots = 256).
+constexpr int kMergeSlots = 144;
+__global__ void tile_heads_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint8_t *__restrict__ head) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j0 = c * kUnitQueries;
+    if (j0 >= n) return;
+    const uint32_t j1 = j0 + kUnitQueries < n ? j0 + kUnitQueries : n;
+    uint32_t prev = keys[j0] >> 3;
+    int lx = (int)(prev >> 18), ly = (int)((prev >> 9) & 511u), lz = (int)(prev & 511u), hx = lx, hy = ly, hz = lz;
+    head[j0] = 1;
+    for (uint32_t j = j0 + 1; j < j1; ++j) {
+        const uint32_t cell = keys[j] >> 3;
+        uint8_t h = 0;
+        if (cell != prev) {
+            prev = cell;
+            const int x = (int)(cell >> 18), y = (int)((cell >> 9) & 511u), z = (int)(cell & 511u);
+            const int nlx = min(lx, x), nhx = max(hx, x), nly = min(ly, y), nhy = max(hy, y), nlz = min(lz, z), nhz = max(hz, z);
+            if ((2 * (nhx - nlx) + 4) * (2 * (nhy - nly) + 4) * (2 * (nhz - nlz) + 4) > kMergeSlots) {
+                h = 1;
+                lx = hx = x, ly = hy = y, lz = hz = z;
+            } else {
+                lx = nlx, hx = nhx, ly = nly, hy = nhy, lz = nlz, hz = nhz;
+            }
+        }
+        head[j] = h;
+    }
 }
 
 __global__ void __launch_bounds__(256) tile_gather_kernel(const double4 *__restrict__ frame, uint32_t n, Pose guess, int apply,
-                                                          const uint32_t *__restrict__ keys, const uint32_t *__restrict__ perm,
+                                                          const uint8_t *__restrict__ head, const uint32_t *__restrict__ perm,
                                                           double4 *__restrict__ src, uint32_t *__restrict__ tile_heads) {
     __shared__ uint32_t s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
@@ -77,7 +106,7 @@ __global__ void __launch_bounds__(256) tile_gather_kernel(const double4 *__restr
             double x = s.x, y = s.y, z = s.z;
             if (apply) pose_act(guess, s.x, s.y, s.z, x, y, z);
             src[j] = make_double4(x, y, z, s.w);
-            heads += unit_head(keys, j) ? 1u : 0u;
+            heads += head[j];
         }
     }
 #pragma unroll
@@ -87,7 +116,7 @@ __global__ void __launch_bounds__(256) tile_gather_kernel(const double4 *__restr
     if (threadIdx.x == 0) tile_heads[blockIdx.x] = s_cnt;
 }
 
-__global__ void __launch_bounds__(256) tile_units_kernel(const uint32_t *__restrict__ keys, uint32_t n, const uint32_t *__restrict__ tile_heads,
+__global__ void __launch_bounds__(256) tile_units_kernel(const uint8_t *__restrict__ head_flag, uint32_t n, const uint32_t *__restrict__ tile_heads,
                                                          uint32_t *__restrict__ units, uint32_t *__restrict__ n_units) {
     __shared__ uint32_t s_warp[8];
     __shared__ uint32_t s_base;
@@ -108,7 +137,7 @@ __global__ void __launch_bounds__(256) tile_units_kernel(const uint32_t *__restr
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t e = 0; e < kHeadTile / 256; ++e) {
         const uint32_t j = blockIdx.x * kHeadTile + e * 256 + threadIdx.x;
-        const bool head = j < n && unit_head(keys, j);
+        const bool head = j < n && head_flag[j] != 0;
         const unsigned m = __ballot_sync(0xffffffffu, head);
         __syncthreads();  // s_warp of the previous round has been read
         if (lane == 0) s_warp[warp] = __popc(m);
@@ -151,9 +180,12 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
                 tile_vals_[0].p);
     g_launches.fetch_add(sort_pairs_u32(tile_tmp_.p, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, n, 30, stream_),
                          std::memory_order_relaxed);
-    SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, tile_keys_[1].p, tile_vals_[1].p, src_.p,
+    tile_flag_.ensure(n);
+    const uint32_t chunks = (n32 + kUnitQueries - 1) / kUnitQueries;
+    SAGE_LAUNCH(tile_heads_kernel, (chunks + 127) / 128, 128, 0, stream_, tile_keys_[1].p, n32, tile_flag_.p);
+    SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, tile_flag_.p, tile_vals_[1].p, src_.p,
                 tile_heads_.p);
-    SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_keys_[1].p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);
+    SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_flag_.p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);
 }
 
 }  // namespace sage

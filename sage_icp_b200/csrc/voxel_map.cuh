@@ -185,7 +185,7 @@ private:
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
     // tile search
     DevBuf<uint32_t> tile_keys_[2], tile_vals_[2], tile_units_, tile_heads_, tile_nunits_;
-    DevBuf<uint8_t> tile_tmp_;
+    DevBuf<uint8_t> tile_tmp_, tile_flag_;  // sort scratch; unit-head flag per sorted position
     DevBuf<double> tile_unit_part_;      // [unit][17] sums of one unit
     DevBuf<uint32_t> tile_group_cnt_;    // units of a group that have published their sums
     int tile_grid_ = 0;            // co-resident blocks of the tile kernels

@@ -50,3 +50,15 @@ def test_shard_of_partitions_a_scan():
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 32
     odd = scan[:1001]
     assert sum(len(bench.shard_of(odd, r, 3)) for r in range(3)) == 1001
+
+
+def test_reference_arm_uses_every_host_core_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still run on all the cores the process may use (round 1's
+    N > 1 reference numbers were single-threaded) and say how many."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--map-points", "60000", "--cpu-fraction", "0.02"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert f"{d['cpu_baseline']['cores']} host threads" in d["cpu_baseline"]["sample"]

@@ -279,10 +279,10 @@ def pipeline_leg(sg, device: int, reps: int = 8):
     local[:, 2] -= syn.SENSOR_HEIGHT  # the pipeline's map frame is the first sensor frame: sensor at the origin
     truth = (0.3, 0.1, math.radians(1.0))
     scan = np.ascontiguousarray(syn.make_scan(4242, truth))  # plain numpy memory: pageable
-    gp = sg.SagePipeline(cfg, device=device) if "device" in sg.SagePipeline.__init__.__code__.co_varnames else sg.SagePipeline(cfg)
+    gp = sg.SagePipeline(cfg, device=device)
     ms, pose_g = [], None
     for r in range(reps + 2):
-        gp.reset()
+        gp.reinitialize()
         gp.map().add_points(local)
         n_map = gp.map().num_points()
         t = time.perf_counter()

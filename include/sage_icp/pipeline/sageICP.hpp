@@ -164,20 +164,27 @@ public:
         out.resize(static_cast<size_t>(k));
         return out;
     }
+    // The node calls poses() after every scan (ros/ros2/OdometryServer.cpp:173).  Poses never change once pushed, so the adaptor
+    // keeps the ones it has converted and fetches only the new tail, in ONE bulk C-ABI call (sage_get_poses): O(1) per frame
+    // instead of O(frames) calls.  reinitialize() (fewer poses than cached) drops the cache.
     std::vector<Sophus::SE3d> poses() const {
-        std::vector<Sophus::SE3d> out;
-        if (!handle_) return out;
+        if (!handle_) return {};
         const int64_t n = sage_num_poses(handle_.get());
-        out.reserve(static_cast<size_t>(n));
-        for (int64_t i = 0; i < n; ++i) {
-            double p[7];
-            Check(sage_get_pose(handle_.get(), static_cast<size_t>(i), p));
-            out.push_back(ToSE3(p));
+        if (n < 0) Check(static_cast<int>(n));
+        if (static_cast<size_t>(n) < pose_cache_.size()) pose_cache_.clear();
+        const size_t have = pose_cache_.size(), want = static_cast<size_t>(n) - have;
+        if (want > 0) {
+            std::vector<double> raw(7 * want);
+            const int64_t got = sage_get_poses(handle_.get(), have, raw.data(), want);
+            if (got < 0) Check(static_cast<int>(got));
+            pose_cache_.reserve(static_cast<size_t>(n));
+            for (int64_t i = 0; i < got; ++i) pose_cache_.push_back(ToSE3(raw.data() + 7 * i));
         }
-        return out;
+        return pose_cache_;
     }
     bool reinitialize() {
         if (handle_) Check(sage_reset(handle_.get()));
+        pose_cache_.clear();
         return true;
     }
     // Extension (not in the reference): true = reproduce the reference map's tsl::robin_map behaviour — the far voxels its
@@ -218,6 +225,7 @@ private:
 
     sageConfig config_;
     std::shared_ptr<sage_pipeline> handle_;
+    mutable std::vector<Sophus::SE3d> pose_cache_;  // poses() already converted (copies of a sageICP share the handle, each keeps its own)
 };
 
 }  // namespace sage_icp::pipeline

@@ -109,6 +109,11 @@ int sage_transform_to_last_frame(sage_pipeline *h, const double last_pose[7], co
 /* sageICP::poses() — pipeline/sageICP.hpp:93 */
 int64_t sage_num_poses(sage_pipeline *h);
 int sage_get_pose(sage_pipeline *h, size_t i, double pose_out[7]);
+/* poses()[first ...] in one call: writes min(cap, num_poses - first) poses of 7 doubles each and returns that number
+ * (poses_out == NULL or cap == 0: returns how many there are from `first` on).  The ROS node reads poses() after every scan
+ * (ros/ros2/OdometryServer.cpp:173): with `first` = the number it already holds, that is one call and one pose per frame
+ * instead of one call per pose of the whole drive. */
+int64_t sage_get_poses(sage_pipeline *h, size_t first, double *poses_out, size_t cap);
 /* sageICP::LocalMap() — pipeline/sageICP.hpp:92 -> VoxelHashMap::Pointcloud (core/VoxelHashMap.cpp:132-142).
  * Same point set as the reference; order is device block order, not robin_map iteration order. */
 int64_t sage_local_map(sage_pipeline *h, double *out, size_t cap_points);

@@ -66,7 +66,7 @@ def load_library() -> C.CDLL:
     L.sage_map_create.restype = C.c_void_p
     L.sage_pipeline_map.restype = C.c_void_p
     L.sage_map_stream.restype = C.c_void_p
-    for f in ("sage_last_source", "sage_last_frame_downsample", "sage_num_poses", "sage_local_map", "sage_map_num_voxels",
+    for f in ("sage_last_source", "sage_last_frame_downsample", "sage_num_poses", "sage_get_poses", "sage_local_map", "sage_map_num_voxels",
               "sage_map_num_points", "sage_map_pointcloud", "sage_map_dump", "sage_map_get_correspondences", "sage_preprocess",
               "sage_voxel_downsample", "sage_launch_count"):
         getattr(L, f).restype = C.c_int64
@@ -385,10 +385,17 @@ class SagePipeline:
         self.L.sage_transform_to_last_frame(self.h, _d(last_pose), _d(current_pose), _d(pts), C.c_size_t(len(pts)), _d(out))
         return out
 
-    def poses(self) -> np.ndarray:
-        n = int(self.L.sage_num_poses(self.h)); out = np.empty((n, 7))
-        for i in range(n):
-            self.L.sage_get_pose(self.h, C.c_size_t(i), _d(out[i]))
+    def poses(self, first: int = 0) -> np.ndarray:
+        """poses()[first:] in one bulk call (sage_get_poses)."""
+        n = self._chk(self.L.sage_get_poses(self.h, C.c_size_t(first), None, C.c_size_t(0)), "sage_get_poses")
+        out = np.empty((n, 7))
+        if n:
+            self._chk(self.L.sage_get_poses(self.h, C.c_size_t(first), _d(out), C.c_size_t(n)), "sage_get_poses")
+        return out
+
+    def pose(self, i: int) -> np.ndarray:
+        out = np.empty(7)
+        self._chk(self.L.sage_get_pose(self.h, C.c_size_t(i), _d(out)), "sage_get_pose")
         return out
 
     def map(self) -> SageMap:

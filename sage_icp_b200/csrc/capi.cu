@@ -263,6 +263,17 @@ int sage_get_pose(sage_pipeline *h, size_t i, double pose_out[7]) {
         return 0;
     });
 }
+int64_t sage_get_poses(sage_pipeline *h, size_t first, double *poses_out, size_t cap) {
+    return guarded([&] {
+        const auto &ps = P(h).poses();
+        if (first > ps.size()) throw ArgError("pose index out of range");
+        const size_t avail = ps.size() - first;
+        if (!poses_out || cap == 0) return (long long)avail;  // query: how many poses from `first` on
+        const size_t n = avail < cap ? avail : cap;
+        for (size_t i = 0; i < n; ++i) pose_to_wire(ps[first + i], poses_out + 7 * i);
+        return (long long)n;
+    });
+}
 int64_t sage_local_map(sage_pipeline *h, double *out, size_t cap) {
     return guarded([&] { return P(h).map().pointcloud(out, cap); });
 }

@@ -866,9 +866,10 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
 // launch gap, no host poll between iterations.  Used for the small scans of the pipeline level, where an iteration is ~20 us
 // of work and the gaps were as long as the work (profiles/r01g_streaming.md).  Launched with cudaLaunchCooperativeKernel, which
 // refuses a grid that is not co-resident, so the barrier cannot deadlock.
-__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_persistent_kernel(IterParams p, int max_iterations) {
+__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_persistent_kernel(IterParams p, int max_iterations, int first_apply) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     for (int i = 0; i < max_iterations; ++i) {
+        p.apply_est = i > 0 ? 1 : first_apply;  // first_apply = 0: the caller has already applied the initial guess (tile_prepare)
         nn_search_iteration<false>(p);
         grid.sync();  // block barrier + grid barrier + fence: the new estimate and `done` are visible to every block
         if (*reinterpret_cast<volatile int *>(&p.st->done)) break;
@@ -947,8 +948,20 @@ void VoxelMapGPU::prof_end(int iterations) {
 }
 
 static const void *tile_kernel_ptr(int minb, bool persistent) {
-    if (persistent) return minb == 4 ? (const void *)nn_tile_persistent_kernel<4> : minb == 5 ? (const void *)nn_tile_persistent_kernel<5> : (const void *)nn_tile_persistent_kernel<6>;
-    return minb == 4 ? (const void *)nn_tile_kernel<4> : minb == 5 ? (const void *)nn_tile_kernel<5> : (const void *)nn_tile_kernel<6>;
+    if (persistent) {
+        switch (minb) {
+            case 4: return (const void *)nn_tile_persistent_kernel<4>;
+            case 5: return (const void *)nn_tile_persistent_kernel<5>;
+            case 6: return (const void *)nn_tile_persistent_kernel<6>;
+            default: return (const void *)nn_tile_persistent_kernel<8>;
+        }
+    }
+    switch (minb) {
+        case 4: return (const void *)nn_tile_kernel<4>;
+        case 5: return (const void *)nn_tile_kernel<5>;
+        case 6: return (const void *)nn_tile_kernel<6>;
+        default: return (const void *)nn_tile_kernel<8>;
+    }
 }
 
 static long env_long(const char *name, long dflt) {
@@ -981,7 +994,7 @@ void VoxelMapGPU::init_search_config() {
     tile_stage_cap_ = (uint32_t)env_long("SAGE_TILE_STAGE", 1536);  // records of 16 bytes: 24 KB
     tile_minb_ = (int)env_long("SAGE_TILE_MINB", 5);  // which instantiation: resident blocks per SM the register allocation aims at
     if (tile_minb_ < 4) tile_minb_ = 4;
-    if (tile_minb_ > 6) tile_minb_ = 6;
+    if (tile_minb_ > 6) tile_minb_ = 8;  // 4, 5, 6 or 8 blocks per SM: 128, 96, 80 or 64 registers per thread
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
     const void *k1 = tile_kernel_ptr(tile_minb_, false), *k2 = tile_kernel_ptr(tile_minb_, true);
     SAGE_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -998,6 +1011,7 @@ void VoxelMapGPU::init_search_config() {
     if (tile_grid_ > 0 && tile_min_ < 1) tile_min_ = 1;
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
+    tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 48);  // mean queries per unit below which the per-query kernel takes the scan
     {
         const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
         xchg_timeout_ns_ = (unsigned long long)(t < 1 ? 1 : t) * 1000000000ull;
@@ -1042,13 +1056,19 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
 // mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
 // as given; mode 2: as mode 1 with the search-work counters on.
 void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode,
-                                   double4 *tgt_out, uint8_t *matched_out, int persistent_iters, int iter_index) {
+                                   double4 *tgt_out, uint8_t *matched_out, int persistent_iters, int iter_index, bool pre_transformed) {
     init_search_config();
     if (mode != 0 && tile_min_ > 0 && n >= tile_min_) {
         // correspondences / sums / work counters of the points as given, through the tile search: gather them in cell order
         // (no transform), one nn_tile_kernel launch, results scattered back through the permutation
         src_.ensure(n);
         tile_prepare(src, n, pose_identity(), false);
+        tile_nunits_pin_.ensure(1);
+        SAGE_CUDA(cudaMemcpyAsync(tile_nunits_pin_.p, tile_nunits_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+        SAGE_CUDA(cudaStreamSynchronize(stream_));
+        last_units_ = *tile_nunits_pin_.p;
+    }
+    if (mode != 0 && tile_min_ > 0 && n >= tile_min_ && (size_t)last_units_ * tile_fill_ <= n) {  // same rule as register_frame_dev
         IterParams p;
         fill_params(p, src_.p, n, max_dist, kernel, sem_th, mode, tgt_out, matched_out);
         const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
@@ -1079,11 +1099,13 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     const int auto_probes = n <= 20000 ? 1 : (n <= 90000 ? 3 : 8);
     p.light_probes = light_probes_ >= 0 ? light_probes_ : auto_probes, p.all_warp = all_warp ? 1 : 0;
     p.xchg_tag += (unsigned long long)iter_index;  // exchange number = exchanges completed so far + 1 + iteration
+    if (pre_transformed && iter_index == 0) p.apply_est = 0;  // src already carries the initial guess (sorted by tile_prepare)
 
     const bool prof = mode == 0;
     if (prof) prof_begin();
     if (persistent_iters > 0) {
-        void *args[] = {&p, &persistent_iters};
+        int first_apply = pre_transformed ? 0 : 1;
+        void *args[] = {&p, &persistent_iters, &first_apply};
         SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (mode == 2) {
@@ -1140,11 +1162,22 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     init_search_config();
     // large scans: sort the queries by cell once, then the tile search (search_tile.cuh); the NCCL variant keeps its separate
     // all-reduce + solve launches, so it cannot run the loop in one launch
-    const bool tile = tile_min_ > 0 && n >= tile_min_;
-    if (tile)
+    bool tile = tile_min_ > 0 && n >= tile_min_;
+    bool sorted = false;
+    if (tile) {
         tile_prepare(frame, n, guess, true);
-    else if (n)
+        sorted = true;  // src_ = the queries in cell order, initial guess applied
+        // The tile search pays per unit, so it needs units that are well filled (a scan: tens of queries per cell).  Queries spread
+        // thinly over the map (one per cell: BASELINE configs[4]'s uniform set, a voxel-downsampled cloud) are served better by the
+        // per-query kernel — which takes the sorted array as it is.  The unit count is known once the sort has run.
+        tile_nunits_pin_.ensure(1);
+        SAGE_CUDA(cudaMemcpyAsync(tile_nunits_pin_.p, tile_nunits_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+        SAGE_CUDA(cudaStreamSynchronize(stream_));
+        last_units_ = *tile_nunits_pin_.p;
+        if ((size_t)last_units_ * tile_fill_ > n) tile = false;
+    } else if (n) {
         SAGE_CUDA(cudaMemcpyAsync(src_.p, frame, n * sizeof(double4), cudaMemcpyDeviceToDevice, stream_));
+    }
     SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, guess, max_iters, est_th);
     // iterations are launched in batches (kernels of a finished registration return at once) and `done` is polled between
     // batches; the first batch is sized from the previous registration so that the common case needs one round trip
@@ -1155,7 +1188,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
         persistent = true;
     } else if (!tile && n <= persistent_max_ && comm_ == nullptr && peer_world_ <= 1 && !dbg_on_) {
         // small scans, single rank: the whole loop in one cooperative launch (nn_search_persistent_kernel)
-        launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, max_iters);
+        launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, max_iters, 0, sorted);
         persistent = true;
     }
     if (persistent) {
@@ -1172,7 +1205,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
             if (tile)
                 launch_tile(n, max_dist, kernel, sem_th, launched + b, 0);
             else
-                launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, 0, launched + b);
+                launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, 0, launched + b, sorted);
         }
         launched += batch;
         SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));

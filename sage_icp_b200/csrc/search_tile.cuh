@@ -33,7 +33,7 @@ constexpr int kTileThreads = 128;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kTileSlots = 2 * kTileThreads;  // region voxels per unit (two table probes per thread)
 constexpr int kTileCols = kTileThreads / 4;   // columns of a unit's sums (four threads share one, through two shuffles)
-constexpr int kTilePairs = 512;               // (query, bucket) pairs per pooled round
+constexpr int kTilePairs = 256;               // (query, bucket) pairs per pooled round
 constexpr int kTileGroup = 16;                // units per group of the two-level, fixed-order sum
 constexpr uint32_t kNotStaged = 0xffffffffu;
 static_assert(kTileCols == 32, "a unit's sums are reduced by one warp per sum");

@@ -127,7 +127,7 @@ private:
     void reserve(size_t extra_points);  // make room for up to `extra_points` new voxels
     void rebuild_table(uint32_t new_cap);
     void launch_iteration(double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
-                          uint8_t *matched_out, int persistent_iters = 0, int iter_index = 0);
+                          uint8_t *matched_out, int persistent_iters = 0, int iter_index = 0, bool pre_transformed = false);
     void fill_params(IterParams &p, double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
                      uint8_t *matched_out);
     // tile search (search_tile.cuh, tile_sort.cu): sort + unit list once per registration, then one launch per iteration or one
@@ -193,6 +193,9 @@ private:
     size_t tile_min_ = 0;          // scans of at least this many queries take the tile search (0 = never)
     uint32_t tile_stage_cap_ = 0;  // staging area of a block, in 16-byte records
     bool tile_persistent_ = true;  // whole GN loop in one cooperative launch
+    size_t tile_fill_ = 48;        // mean queries per unit the tile search needs to beat the per-query kernel
+    uint32_t last_units_ = 0;      // units of the last sorted scan
+    PinBuf<uint32_t> tile_nunits_pin_;
     bool coop_ok_ = false;
     int light_probes_ = -1;  // < 0: chosen from the number of queries (launch_iteration); SAGE_LIGHT_PROBES overrides
     bool dbg_on_ = false;

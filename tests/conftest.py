@@ -36,16 +36,17 @@ def pytest_collection_modifyitems(config, items):
 # use this fixture run once per schedule.  The library reads these variables when a map first searches (registration.cu).
 SEARCH_MODES = {
     "default": {},                                                              # tile search from 16 384 queries up
-    "tile": {"SAGE_TILE_MIN": "1"},                                             # tile search for every size, persistent loop
-    "tile_launch": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PERSISTENT": "0", "SAGE_TILE_MINB": "6"},  # one launch per iteration, 80 registers
-    "tile_spill": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "96", "SAGE_TILE_MINB": "4"},       # staging area too small: global scans
+    # tile search forced for every size and density (SAGE_TILE_FILL=0 switches off the "units must be well filled" rule)
+    "tile": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0"},                                      # persistent loop, 96 registers
+    "tile_launch": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0", "SAGE_TILE_PERSISTENT": "0", "SAGE_TILE_MINB": "8", "SAGE_TILE_STAGE": "704"},
+    "tile_spill": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0", "SAGE_TILE_STAGE": "96", "SAGE_TILE_MINB": "4"},  # staging too small: global scans
     "legacy": {"SAGE_TILE": "0"},                                               # thread-per-query + deferred warp phase only
 }
 
 
 @pytest.fixture(params=list(SEARCH_MODES))
 def search_mode(request, monkeypatch):
-    for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
+    for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
         monkeypatch.delenv(k, raising=False)
     for k, v in SEARCH_MODES[request.param].items():
         monkeypatch.setenv(k, v)

@@ -1,6 +1,7 @@
-"""BASELINE configs[1] at FULL size (120 000 queries, 5 M-point map): the oracle cannot register the full scan in seconds, so
-parity is checked on a 1/20 sample of the queries against the same full map, and the full run through properties the
-domain offers: permutation invariance of the pose, a zero step from the converged pose, and shard additivity of the sums."""
+"""BASELINE configs[1] at FULL size (120 000 queries, 5 M-point map): every query's correspondence bit for bit and the full
+10-iteration registration against the oracle on all host cores (~0.1 s per pass), plus the properties the domain offers:
+permutation invariance of the pose, a zero step from the converged pose, shard additivity of the sums; and a full-size drive of
+the `gt` launch-file variant (sem_th = 0.05) through the pipeline."""
 import numpy as np
 import pytest
 
@@ -28,15 +29,60 @@ def test_full_map_same_voxels_and_points(world):
     assert g.num_points() == o.num_points() > 4_900_000
 
 
-def test_sampled_queries_against_the_full_map(world, orc):
+def _threads():
+    import os
+    return max(1, len(os.sched_getaffinity(0)))
+
+
+@pytest.mark.parametrize("sem_th", [0.4, 0.05])
+def test_every_query_of_the_full_scan_bit_exact(world, sem_th):
+    """GetCorrespondences for ALL 120 000 queries of the bench scan against the 5 M-point map: the same matched set and, for every
+    matched query, the same target record as the oracle's f64 scan of all 27 voxels (core/VoxelHashMap.cpp:48-130)."""
     import bench
     g, o, scan, guess = world
-    sub = np.ascontiguousarray(scan[::20])
-    pose_o, it_o = o.register_frame_core(sub, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH, threads=orc.max_threads(), max_iters=10, est_th=0.0)
-    pose_g, it_g = g.register_frame(sub, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH, max_iters=10, est_th=0.0)
+    q = bench.transform_by_guess(scan, guess)
+    tgt, matched = g.get_correspondences(q, bench.MAX_DIST, sem_th)
+    _, tgt_o, qidx = o.get_correspondences(q, bench.MAX_DIST, sem_th, threads=_threads())
+    m_o = np.zeros(len(q), bool)
+    m_o[qidx] = True
+    assert len(q) == 120_000 and m_o.sum() > 100_000
+    assert np.array_equal(matched.astype(bool), m_o)
+    assert np.array_equal(tgt[m_o], tgt_o)
+
+
+def test_full_scan_registration_against_the_oracle(world):
+    """The bench step itself — 120 000 queries, 10 Gauss-Newton iterations — on both sides: rounding-level agreement."""
+    import bench
+    g, o, scan, guess = world
+    pose_o, it_o = o.register_frame_core(scan, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH, threads=_threads(), max_iters=10, est_th=0.0)
+    pose_g, it_g = g.register_frame(scan, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH, max_iters=10, est_th=0.0)
     dt, da = pose_delta(pose_g, pose_o)
     assert it_g == it_o == 10 and dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (dt, da)
-    assert dt < 1e-9
+    assert dt < 1e-9 and da < 1e-10
+    # and with the reference's own stopping rule
+    pose_o, it_o = o.register_frame_core(scan, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH, threads=_threads())
+    pose_g, it_g = g.register_frame(scan, guess, bench.MAX_DIST, bench.KERNEL, bench.SEM_TH)
+    dt, da = pose_delta(pose_g, pose_o)
+    assert it_g == it_o and dt < 1e-9 and da < 1e-10, (it_g, it_o, dt, da)
+
+
+def test_gt_variant_full_size_drive(orc):
+    """ros/launch/odometry_gt.launch.py (sem_th = 0.05, dynamic filter off) through sageICP::RegisterFrame on full 64 x 1875 scans."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config(sem_th=0.05)
+    gp, op = sg.SagePipeline(cfg), orc.OraclePipeline(cfg, threads=_threads(), evict_faithful=False)
+    n = 25
+    traj = syn.trajectory(n)
+    for i in range(n):
+        scan = syn.make_scan(300 + i, tuple(traj[i]))
+        pg, _, _ = gp.register_frame(scan)
+        po, _, _ = op.register_frame(scan)
+        dt, da = pose_delta(pg, po)
+        assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (i, dt, da)
+        assert gp.last_iterations() == op.last_iterations(), i
+        assert np.array_equal(gp.last_source(), op.last_source()), i
 
 
 def test_full_scan_properties(world):

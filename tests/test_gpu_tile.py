@@ -14,8 +14,10 @@ BASIC_LABELS = [40, 44, 48, 49, 50, 70, 72]
 def _maps(orc, pts, monkeypatch=None, env=None):
     import sage_icp_b200 as sg
     if env is not None:
-        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
+        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
             monkeypatch.delenv(k, raising=False)
+        if env.get("SAGE_TILE_MIN") == "1":
+            monkeypatch.setenv("SAGE_TILE_FILL", "0")  # forced for every density
         for k, v in env.items():
             monkeypatch.setenv(k, v)
     g = sg.SageMap(0.8, 1e9, 20, 20, BASIC_LABELS)
@@ -44,8 +46,8 @@ def _check_corr(g, o, q, max_dist, th):
     return int(matched.sum())
 
 
-@pytest.mark.parametrize("env", [{}, {"SAGE_TILE_STAGE": "128"}, {"SAGE_TILE_MINB": "4"}, {"SAGE_TILE_MINB": "6", "SAGE_TILE_BLOCKS": "2"}],
-                         ids=["default", "tiny_staging", "128_registers", "80_registers_2_blocks_per_sm"])
+@pytest.mark.parametrize("env", [{}, {"SAGE_TILE_STAGE": "128"}, {"SAGE_TILE_MINB": "4"}, {"SAGE_TILE_MINB": "8", "SAGE_TILE_BLOCKS": "2"}],
+                         ids=["default", "tiny_staging", "128_registers", "64_registers_2_blocks_per_sm"])
 def test_tile_correspondences_bit_exact_on_a_full_scan(orc, monkeypatch, env):
     """32 000 queries of a street scan (above the 16 384-query threshold): every query's target equals the oracle's, in the
     caller's order, whether the buckets fit the staging area or are scanned from global memory, for each register budget."""

@@ -12,12 +12,15 @@ CONFIGS = {
     "tile_launch_per_iter": {"SAGE_TILE_MIN": "1", "SAGE_TILE_PERSISTENT": "0"},
     "tile_minb4": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "4"},
     "tile_minb6_stage1024": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "6", "SAGE_TILE_STAGE": "1024"},
+    "tile_minb8_stage704": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "8", "SAGE_TILE_STAGE": "704"},
+    "tile_minb6_stage1408": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "6", "SAGE_TILE_STAGE": "1408"},
+    "tile_minb4_stage2560": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "4", "SAGE_TILE_STAGE": "2560"},
     "tile_minb5_stage1024": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "5", "SAGE_TILE_STAGE": "1024"},
     "tile_stage2048": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "2048"},
     "tile_blocks4": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "4"},
     "tile_blocks3": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "3"},
 }
-KEYS = ("SAGE_TILE", "SAGE_POOLED", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_PROBES", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS")
+KEYS = ("SAGE_TILE", "SAGE_TILE_FILL", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS")
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CONFIGS)
 sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2000, 8000, 15000, 30000, 60000, 120000]
 n_map = int(sys.argv[3]) if len(sys.argv) > 3 else 5_000_000
@@ -29,6 +32,8 @@ for name in which:
     for k in KEYS:
         os.environ.pop(k, None)
     os.environ.update(CONFIGS[name])
+    if CONFIGS[name].get("SAGE_TILE_MIN") == "1":
+        os.environ["SAGE_TILE_FILL"] = "0"
     m = sg.SageMap(0.8, 1e9, 20, 20, bench.BASIC_LABELS)
     m.add_points(pts)
     for n in sizes:
@@ -57,7 +62,7 @@ if os.environ.get("TILE_TIMELINE", "1") != "0":
     import ctypes as C
     for k in KEYS:
         os.environ.pop(k, None)
-    os.environ.update({"SAGE_TILE_MIN": "1"})
+    os.environ.update({"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0"})
     if len(sys.argv) > 4:
         os.environ.update(dict(kv.split("=") for kv in sys.argv[4].split(",")))
     m = sg.SageMap(0.8, 1e9, 20, 20, bench.BASIC_LABELS)
@@ -78,6 +83,9 @@ if os.environ.get("TILE_TIMELINE", "1") != "0":
     print(f"tile timeline: {len(b)} blocks, start spread {b[:,0].max()-t0} ns, block end (before finish) med {np.median(b[:,9]-t0):.0f} p90 "
           f"{np.percentile(b[:,9]-t0,90):.0f} max {(b[:,9]-t0).max()} ns; units/block med {np.median(b[:,10]):.1f} max {b[:,10].max()}, "
           f"queries/block med {np.median(b[:,11]):.0f} max {b[:,11].max()}")
+    tail = buf[K * g:K * g + 8].astype(np.int64)
+    print(f"   last block: enters reduce {tail[0]-t0} ns, sums reduced/exchanged +{tail[1]-tail[0]}, 6x6 solved +{tail[5]-tail[1]}, exp +{tail[6]-tail[5]}, "
+          f"step done +{tail[2]-tail[6]} (total {tail[2]-tail[0]} ns)")
     for k, nm in names.items():
         print(f"   {nm:24s}: per block total ns: median {np.median(b[:,k]):8.0f} p90 {np.percentile(b[:,k],90):8.0f} max {b[:,k].max():8d} | "
               f"per unit mean {b[:,k].sum()/max(1,b[:,10].sum()):7.0f}")

@@ -107,6 +107,14 @@ int sage_get_prediction_model(sage_pipeline *h, double pose_out[7]);
 int sage_transform_to_last_frame(sage_pipeline *h, const double last_pose[7], const double current_pose[7],
                                  const double *xyzl, size_t n, double *out);
 /* sageICP::poses() — pipeline/sageICP.hpp:93 */
+/* The node's key-frame test on the device (ros/ros2/OdometryServer.cpp:222-241):
+ *   grid_out[rows][cols] = utils::EigenToGridMap(points, bounds, {rows, cols})              ros/ros2/Utils.hpp:220-242
+ *   with last_pose/current_pose (both or neither): of TransformToLastFrame(last, current, points) pipeline/sageICP.cpp:123-129
+ *   with last_occ: *overlap_out = utils::compute_occ_overlap(last_occ, that grid)           ros/ros2/Utils.hpp:244-258
+ * bounds = {x0, x1, y0, y1, z0, z1} (key_frame_bounds flattened); grids are row-major int32 0/1 like the reference's
+ * vector<vector<int>>; grid_out may be NULL when only the overlap is wanted.  The points cross PCIe once. */
+int sage_key_frame_grid(sage_pipeline *h, const double *xyzl, size_t n, const double *last_pose, const double *current_pose,
+                        const double bounds[6], int rows, int cols, const int32_t *last_occ, int32_t *grid_out, double *overlap_out);
 int64_t sage_num_poses(sage_pipeline *h);
 int sage_get_pose(sage_pipeline *h, size_t i, double pose_out[7]);
 /* poses()[first ...] in one call: writes min(cap, num_poses - first) poses of 7 doubles each and returns that number

@@ -180,6 +180,15 @@ size_t orc_map_get_correspondences(void *m, const double *xyzl, size_t n, double
     if (qidx) std::memcpy(qidx, c.query_index.data(), c.query_index.size() * sizeof(int64_t));
     return c.source.size();
 }
+// key-frame occupancy grid / overlap of the ROS node (ros/ros2/Utils.hpp:220-258); bounds6 = {x0,x1,y0,y1,z0,z1}
+void orc_grid_map(const double *xyzl, size_t n, const double *bounds6, int H, int W, int32_t *grid_out) {
+    const double b[3][2] = {{bounds6[0], bounds6[1]}, {bounds6[2], bounds6[3]}, {bounds6[4], bounds6[5]}};
+    const auto g = EigenToGridMap(to_cloud(xyzl, n), b, H, W);
+    for (size_t i = 0; i < g.size(); ++i) grid_out[i] = g[i];
+}
+double orc_occ_overlap(const int32_t *occ_s, const int32_t *occ_t, size_t cells) {
+    return ComputeOccOverlap(std::vector<int>(occ_s, occ_s + cells), std::vector<int>(occ_t, occ_t + cells));
+}
 // exact occupancy statistics for the algorithmic-bytes formula: sum over queries of occupied
 // neighbour voxels and of candidate points.
 void orc_map_nn_stats(void *m, const double *xyzl, size_t n, uint64_t *occupied, uint64_t *candidates) {

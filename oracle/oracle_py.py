@@ -44,7 +44,7 @@ def lib() -> C.CDLL:
                   "orc_map_pointcloud", "orc_map_dump", "orc_map_get_correspondences", "orc_last_source",
                   "orc_last_frame_downsample", "orc_num_poses", "orc_local_map", "orc_robin_order", "orc_voxelize", "orc_deskew"):
             getattr(L, f).restype = C.c_size_t
-        for f in ("orc_get_adaptive_threshold", "orc_last_sigma", "orc_rotation_angle"):
+        for f in ("orc_get_adaptive_threshold", "orc_last_sigma", "orc_rotation_angle", "orc_occ_overlap"):
             getattr(L, f).restype = C.c_double
         L.orc_voxel_hash.restype = C.c_uint32
         _lib = L
@@ -133,6 +133,19 @@ def align_clouds(src, tgt, th, threads=1):
     JTJ, JTr, x, est = np.empty((6, 6)), np.empty(6), np.empty(6), np.empty(7)
     lib().orc_align_clouds(_d(src), _d(tgt), C.c_size_t(len(src)), C.c_double(th), C.c_int(threads), _d(JTJ), _d(JTr), _d(x), _d(est))
     return JTJ, JTr, x, est
+
+
+def grid_map(pts, bounds, rows: int, cols: int) -> np.ndarray:
+    """utils::EigenToGridMap (ros/ros2/Utils.hpp:220-242)."""
+    pts = _c64(pts); b = _c64(np.asarray(bounds, float).reshape(6)); out = np.zeros((rows, cols), np.int32)
+    lib().orc_grid_map(_d(pts), C.c_size_t(len(pts)), _d(b), rows, cols, out.ctypes.data_as(_ip))
+    return out
+
+
+def occ_overlap(occ_s, occ_t) -> float:
+    """utils::compute_occ_overlap (ros/ros2/Utils.hpp:244-258)."""
+    a, b = np.ascontiguousarray(occ_s, np.int32), np.ascontiguousarray(occ_t, np.int32)
+    return float(lib().orc_occ_overlap(a.ctypes.data_as(_ip), b.ctypes.data_as(_ip), C.c_size_t(a.size)))
 
 
 def deskew(frame, ts, start, finish) -> np.ndarray:

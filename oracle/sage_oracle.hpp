@@ -157,6 +157,36 @@ inline Cloud PreprocessDynamic(const Cloud &frame, double max_range, double min_
     return inliers;
 }
 
+// EigenToGridMap — ros/ros2/Utils.hpp:220-242 (the node's key-frame occupancy grid; row-major H x W of 0/1).
+// bounds = key_frame_bounds: {{x0,x1},{y0,y1},{z0,z1}}; occ_size = {H, W}.
+inline std::vector<int> EigenToGridMap(const Cloud &points, const double bounds[3][2], int H, int W) {
+    std::vector<int> gridMap((size_t)H * (size_t)W, 0);
+    const double x_resolution = (bounds[0][1] - bounds[0][0]) / W;  // Width
+    const double y_resolution = (bounds[1][1] - bounds[1][0]) / H;  // Height
+    for (const auto &point : points) {
+        if (point.x < bounds[0][0] || point.x > bounds[0][1] || point.y < bounds[1][0] || point.y > bounds[1][1] || point.z < bounds[2][0] ||
+            point.z > bounds[2][1]) {
+            continue;
+        }
+        // move pc to occ frame (the reference adds the UPPER bound, :233-234)
+        const double fx = (point.x + bounds[0][1]) / x_resolution, fy = (point.y + bounds[1][1]) / y_resolution;
+        if (!(fx > -2147483648.0 && fx < 2147483648.0 && fy > -2147483648.0 && fy < 2147483648.0)) continue;  // static_cast<int> would be UB
+        const int occ_x = static_cast<int>(fx);
+        const int occ_y = static_cast<int>(fy);
+        if (occ_x >= 0 && occ_x < W && occ_y >= 0 && occ_y < H) gridMap[(size_t)occ_y * W + occ_x] = 1;
+    }
+    return gridMap;
+}
+// compute_occ_overlap — ros/ros2/Utils.hpp:244-258
+inline double ComputeOccOverlap(const std::vector<int> &occ_s, const std::vector<int> &occ_t) {
+    int overlap = 0, total = 0;
+    for (size_t i = 0; i < occ_s.size(); i++) {
+        if (occ_s[i] == 1 && occ_t[i] == 1) overlap++;
+        if (occ_s[i] == 1) total++;
+    }
+    return static_cast<double>(overlap) / total;
+}
+
 // VoxelDownsample — core/Preprocessing.cpp:44-84. The first `len` maps of grid_group are default-constructed
 // (bucket_count 0, unreserved, :50); the reserved copies appended at :52-56 are never used.
 inline Cloud VoxelDownsample(const Cloud &frame, const std::vector<std::vector<int>> &voxel_labels,

@@ -385,6 +385,18 @@ class SagePipeline:
         self.L.sage_transform_to_last_frame(self.h, _d(last_pose), _d(current_pose), _d(pts), C.c_size_t(len(pts)), _d(out))
         return out
 
+    def key_frame_grid(self, pts, bounds, rows: int, cols: int, last_pose=None, current_pose=None, last_occ=None):
+        """utils::EigenToGridMap (+ TransformToLastFrame first, + compute_occ_overlap against last_occ) on the device.
+        Returns (grid[rows, cols] int32, overlap or None)."""
+        pts = _pts(pts); b = _c64(np.asarray(bounds, float).reshape(6)); grid = np.zeros((rows, cols), np.int32); ov = C.c_double()
+        lp = None if last_pose is None else _d(_c64(last_pose))
+        cp = None if current_pose is None else _d(_c64(current_pose))
+        lo = None if last_occ is None else np.ascontiguousarray(last_occ, np.int32)
+        self._chk(self.L.sage_key_frame_grid(self.h, _d(pts), C.c_size_t(len(pts)), lp, cp, _d(b), rows, cols,
+                                             None if lo is None else lo.ctypes.data_as(_ip), grid.ctypes.data_as(_ip), C.byref(ov)),
+                  "sage_key_frame_grid")
+        return grid, (float(ov.value) if lo is not None else None)
+
     def poses(self, first: int = 0) -> np.ndarray:
         """poses()[first:] in one bulk call (sage_get_poses)."""
         n = self._chk(self.L.sage_get_poses(self.h, C.c_size_t(first), None, C.c_size_t(0)), "sage_get_poses")

@@ -252,6 +252,19 @@ int sage_transform_to_last_frame(sage_pipeline *h, const double last_pose[7], co
     }
     return 0;
 }
+int sage_key_frame_grid(sage_pipeline *h, const double *xyzl, size_t n, const double *last_pose, const double *current_pose,
+                        const double bounds[6], int rows, int cols, const int32_t *last_occ, int32_t *grid_out, double *overlap_out) {
+    return (int)guarded([&] {
+        need(bounds, "bounds");
+        if (!xyzl && n) throw ArgError("null argument: xyzl");
+        if ((last_pose == nullptr) != (current_pose == nullptr)) throw ArgError("last_pose and current_pose go together");
+        if (last_occ && !overlap_out) throw ArgError("null argument: overlap_out");
+        Pose a, b;
+        if (last_pose) a = pose_from_wire(last_pose), b = pose_from_wire(current_pose);
+        P(h).key_frame_grid(xyzl, n, last_pose ? &a : nullptr, last_pose ? &b : nullptr, bounds, rows, cols, last_occ, grid_out, overlap_out);
+        return 0;
+    });
+}
 int64_t sage_num_poses(sage_pipeline *h) {
     return guarded([&] { return (long long)P(h).poses().size(); });
 }

@@ -617,6 +617,57 @@ void FrontEnd::unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t po
                 label_is_f32, out);
 }
 
+// Key-frame occupancy grid of the ROS node (utils::EigenToGridMap, ros/ros2/Utils.hpp:220-242), optionally of the points moved into
+// the last key frame first (sageICP::TransformToLastFrame -> TransformPoints, pipeline/sageICP.cpp:123-129), and the overlap ratio
+// against a previous grid (utils::compute_occ_overlap, Utils.hpp:244-258).  One thread per point; cells are 0/1, so plain stores race
+// benignly; the two counts are integer atomics (exact, order-independent).
+__global__ void occ_grid_kernel(const double4 *pts, uint32_t n, Pose T, int apply, OccGridParams g, int32_t *grid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 p = pts[i];
+    double x = p.x, y = p.y, z = p.z;
+    if (apply) pose_act(T, p.x, p.y, p.z, x, y, z);
+    // if (point[k] < lo || point[k] > hi) continue;  (Utils.hpp:227-231; NaN compares false on both sides and goes on, as there)
+    if (x < g.x0 || x > g.x1 || y < g.y0 || y > g.y1 || z < g.z0 || z > g.z1) return;
+    // int occ_x = static_cast<int>((point[0] + bounds[0][1]) / x_resolution);  (:233-234: the UPPER bound is added, as written)
+    const double fx = __ddiv_rn(__dadd_rn(x, g.x1), g.x_res), fy = __ddiv_rn(__dadd_rn(y, g.y1), g.y_res);
+    if (!(fx > -2147483648.0 && fx < 2147483648.0 && fy > -2147483648.0 && fy < 2147483648.0)) return;  // int conversion would be UB there
+    const int ox = __double2int_rz(fx), oy = __double2int_rz(fy);
+    if (ox >= 0 && ox < g.cols && oy >= 0 && oy < g.rows) grid[(size_t)oy * g.cols + ox] = 1;
+}
+__global__ void occ_overlap_kernel(const int32_t *occ_s, const int32_t *occ_t, uint32_t cells, unsigned *counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool s1 = i < cells && occ_s[i] == 1;
+    const unsigned both = __ballot_sync(0xffffffffu, s1 && occ_t[i] == 1), tot = __ballot_sync(0xffffffffu, s1);
+    if ((threadIdx.x & 31) == 0) {
+        if (both) atomicAdd(counts, (unsigned)__popc(both));
+        if (tot) atomicAdd(counts + 1, (unsigned)__popc(tot));
+    }
+}
+
+void FrontEnd::key_frame_grid(const double4 *pts, size_t n, const Pose *T, const OccGridParams &g, const int32_t *last_occ_host, int32_t *grid_host,
+                              double *overlap) {
+    SAGE_CUDA(cudaSetDevice(device_));
+    const size_t cells = (size_t)g.rows * g.cols;
+    occ_.ensure(2 * cells + 2);
+    int32_t *cur = reinterpret_cast<int32_t *>(occ_.p), *last = cur + cells;
+    unsigned *counts = reinterpret_cast<unsigned *>(occ_.p + 2 * cells);
+    SAGE_CUDA(cudaMemsetAsync(cur, 0, cells * sizeof(int32_t), stream_));
+    if (n)
+        SAGE_LAUNCH(occ_grid_kernel, fe_blocks(n), kFeThreads, 0, stream_, pts, (uint32_t)n, T ? *T : pose_identity(), T ? 1 : 0, g, cur);
+    if (last_occ_host) {
+        SAGE_CUDA(cudaMemcpyAsync(last, last_occ_host, cells * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+        SAGE_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned), stream_));
+        SAGE_LAUNCH(occ_overlap_kernel, fe_blocks(cells), kFeThreads, 0, stream_, last, cur, (uint32_t)cells, counts);
+    }
+    unsigned c[2] = {0, 0};
+    if (grid_host) SAGE_CUDA(cudaMemcpyAsync(grid_host, cur, cells * sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+    if (last_occ_host) SAGE_CUDA(cudaMemcpyAsync(c, counts, sizeof(c), cudaMemcpyDeviceToHost, stream_));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    // return static_cast<double>(overlap) / total;  (Utils.hpp:257: 0 / 0 = NaN when the last grid is empty, as there)
+    if (overlap) *overlap = last_occ_host ? (double)c[0] / (double)c[1] : 0.0;
+}
+
 void FrontEnd::deskew(const double4 *in, const double *ts, size_t n, const Pose &start, const Pose &finish, double4 *out) {
     SAGE_CUDA(cudaSetDevice(device_));
     if (n == 0) return;

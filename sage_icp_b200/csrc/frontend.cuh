@@ -27,6 +27,12 @@ struct DynFilterParams {  // Preprocess' dynamic-vehicle branch (core/Preprocess
     double dy_th;             // dynamic_vehicle_filter_th
 };
 
+struct OccGridParams {  // utils::EigenToGridMap (ros/ros2/Utils.hpp:220-242): bounds [[x0,x1],[y0,y1],[z0,z1]], H x W cells
+    double x0, x1, y0, y1, z0, z1;
+    double x_res, y_res;  // (x1 - x0) / cols, (y1 - y0) / rows
+    int rows, cols;
+};
+
 struct CropParams {
     int enabled;
     double max_range, min_range, label_max_range;
@@ -54,6 +60,9 @@ public:
     // utils::PointCloud2ToEigen (ros/ros2/Utils.hpp:161-180) on the device: packed records -> x, y, z, label as f64
     void unpack_pointcloud2(const uint8_t *data_dev, size_t n, uint32_t point_step, uint32_t x_off, uint32_t y_off, uint32_t z_off,
                             uint32_t label_off, int label_is_f32, double4 *out);
+    // Key-frame occupancy grid (+ overlap against `last_occ_host` when given) of a device-resident cloud; T: transform applied first.
+    void key_frame_grid(const double4 *pts, size_t n, const Pose *T, const OccGridParams &g, const int32_t *last_occ_host, int32_t *grid_host,
+                        double *overlap);
     // DeSkewScan on the device (in place allowed).
     void deskew(const double4 *in, const double *timestamps_dev, size_t n, const Pose &start, const Pose &finish, double4 *out);
 
@@ -75,6 +84,7 @@ private:
     DevBuf<unsigned long long> dyn_key_[2];  // cluster-order sort of the kept vehicle points
     DevBuf<uint32_t> dyn_val_[2];
     DevBuf<uint8_t> sort_tmp_;
+    DevBuf<int32_t> occ_;  // key-frame grids: current, last, two counters
     PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_[2];
     int parity_ = 0;
     std::vector<std::vector<uint32_t>> group_members_, group_hashes_, group_order_;

@@ -60,6 +60,20 @@ void Pipeline::reset_threshold() {
     model_deviation_ = pose_identity();
 }
 
+void Pipeline::key_frame_grid(const double *xyzl, size_t n, const Pose *last, const Pose *current, const double bounds[6], int rows, int cols,
+                              const int32_t *last_occ, int32_t *grid_out, double *overlap) {
+    if (rows < 1 || cols < 1 || (long long)rows * cols > (1ll << 26)) throw ArgError("key-frame grid: rows/cols out of range");
+    OccGridParams g;
+    g.x0 = bounds[0], g.x1 = bounds[1], g.y0 = bounds[2], g.y1 = bounds[3], g.z0 = bounds[4], g.z1 = bounds[5];
+    g.rows = rows, g.cols = cols;
+    g.x_res = (g.x1 - g.x0) / cols;  // Width  (Utils.hpp:224)
+    g.y_res = (g.y1 - g.y0) / rows;  // Height (Utils.hpp:225)
+    Pose T;
+    const bool move = last && current;
+    if (move) T = pose_mul(pose_inverse(*last), *current);  // last_pose.inverse() * current_pose, pipeline/sageICP.cpp:127
+    fe_.key_frame_grid(map_.stage_points(xyzl, n), n, move ? &T : nullptr, g, last_occ, grid_out, overlap);
+}
+
 void Pipeline::reinitialize() {  // pipeline/sageICP.hpp:94-99
     poses_.clear();
     reset_threshold();

@@ -25,6 +25,11 @@ public:
     long long preprocess_host(const double *xyzl, size_t n, std::vector<double> &out);
     long long downsample_host(const double *xyzl, size_t n, double scale, std::vector<double> &out);
 
+    // the node's key-frame test (ros/ros2/OdometryServer.cpp:222-241): grid of `points` (moved by last^-1 * current when both are
+    // given) and, when last_occ is given, its overlap with that grid
+    void key_frame_grid(const double *xyzl, size_t n, const Pose *last, const Pose *current, const double bounds[6], int rows, int cols,
+                        const int32_t *last_occ, int32_t *grid_out, double *overlap);
+
     const std::vector<Pose> &poses() const { return poses_; }
     VoxelMapGPU &map() { return map_; }
     void last_source(std::vector<double> &out) { fetch(src_.p, n_src_, out); }

@@ -162,11 +162,11 @@ __device__ __forceinline__ Pose load_pose_cg(const Pose *q) {
 // The step is a chain of dependent f64 operations (two divisions, sqrt, sin/cos, atan2: ~8 us in one thread), so the independent
 // pieces run side by side in two warps: [solve] -> [rotation part of exp | translation part of exp] -> [pose product | log norm]
 // -> [stop test; the final pose only when the loop ends].  Same formulas, same operation order as pose_exp / pose_log.
-__device__ __forceinline__ void icp_step_block(IcpState *st, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
+__device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
     __shared__ double s_xi[6];
     if (threadIdx.x == 0) {
         double xi[6];
-        icp_solve_xi(st->sums, xi);
+        icp_solve_xi(sums, xi);
 #pragma unroll
         for (int i = 0; i < 6; ++i) s_xi[i] = xi[i];
         if (dbg) dbg[5] = gtime();
@@ -254,7 +254,7 @@ __global__ void icp_solve_kernel(IcpState *st) {  // <<<1, 64>>>, after the NCCL
     __shared__ Pose s_pose;
     __shared__ double s_norm;
     if (st->done) return;
-    icp_step_block(st, &s_pose, &s_norm);
+    icp_step_block(st, st->sums, &s_pose, &s_norm);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -513,6 +513,7 @@ __device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s
 // fixed order (p.partials[k * count + i]), exchange the sums with the other ranks (fused peer-memory all-reduce, `tag` = this
 // iteration's sequence number), take the Gauss-Newton step.  Called by every thread of that block.
 __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t count, Pose &s_est, double &s_norm, unsigned long long tag) {
+    __shared__ double s_sums[kSums];  // the reduced sums stay on chip for the solve (st->sums is the copy the host / the exchange reads)
     IcpState *st = p.st;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
     __threadfence();
@@ -530,7 +531,7 @@ __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t co
         for (; b < count; b += 32) v += __ldcg(pk + b);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) st->sums[k] = v;
+        if (lane == 0) st->sums[k] = v, s_sums[k] = v;
     }
     __syncthreads();
     if (p.xchg_world > 1) {
@@ -545,7 +546,7 @@ __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t co
         if (t < p.xchg_world) {
             double *dst = p.xchg_peer[t] + slot + (size_t)p.xchg_rank * kXchgSlot;
 #pragma unroll
-            for (int k = 0; k < kSums; ++k) dst[k] = st->sums[k];
+            for (int k = 0; k < kSums; ++k) dst[k] = s_sums[k];
             __threadfence_system();
             *reinterpret_cast<volatile unsigned long long *>(dst + kSums) = tag;
         }
@@ -567,7 +568,7 @@ __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t co
             const volatile double *mine = p.xchg_peer[p.xchg_rank] + slot;
             double v = 0;
             for (int r = 0; r < p.xchg_world; ++r) v += mine[(size_t)r * kXchgSlot + t];
-            st->sums[t] = v;
+            st->sums[t] = v, s_sums[t] = v;
         }
         __syncthreads();
     }
@@ -577,7 +578,7 @@ __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t co
         if (p.xchg_world > 1 && st->comm_error) st->done = 1;
     }
     __syncthreads();
-    if (p.solve && !(p.xchg_world > 1 && st->comm_error)) icp_step_block(st, &s_est, &s_norm, p.dbg ? p.dbg + kDbg * gridDim.x : nullptr);
+    if (p.solve && !(p.xchg_world > 1 && st->comm_error)) icp_step_block(st, s_sums, &s_est, &s_norm, p.dbg ? p.dbg + kDbg * gridDim.x : nullptr);
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x + 2] = gtime(), p.dbg[kDbg * gridDim.x + 3] = gridDim.x;
 }
 
@@ -992,7 +993,7 @@ void VoxelMapGPU::init_search_config() {
     // tile search: staging area (dynamic shared memory) + co-resident grid
     static_assert(kTileThreads == 128, "tile_sort.cu cuts units of 128 queries");
     tile_stage_cap_ = (uint32_t)env_long("SAGE_TILE_STAGE", 1536);  // records of 16 bytes: 24 KB
-    tile_minb_ = (int)env_long("SAGE_TILE_MINB", 5);  // which instantiation: resident blocks per SM the register allocation aims at
+    tile_minb_ = (int)env_long("SAGE_TILE_MINB", 4);  // which instantiation: resident blocks per SM the register allocation aims at
     if (tile_minb_ < 4) tile_minb_ = 4;
     if (tile_minb_ > 6) tile_minb_ = 8;  // 4, 5, 6 or 8 blocks per SM: 128, 96, 80 or 64 registers per thread
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);

@@ -2,7 +2,7 @@
 // the ordered array into units for the tile search (search_tile.cuh).  The order is a locality hint only: the tile kernel
 // recomputes every unit's region from the queries' actual voxels each iteration, so a poor order costs time, never correctness.
 //
-//   tile_key_kernel     key = low 9 bits of each cell coordinate + the voxel inside the cell (cells repeat every 512 cells = 819 m
+//   tile_key_kernel     key = low 7 bits of each cell coordinate + the voxel inside the cell (cells repeat every 128 cells = 205 m
 //                       at 0.8 m voxels; two aliasing cells in one run merely make a unit whose region does not fit, which falls
 //                       back to global search)
 //   cub::DeviceRadixSort::SortPairs over the 30 key bits (stable, deterministic: equal inputs give equal unit lists, which is
@@ -42,6 +42,11 @@ int sort_pairs_u64(void *tmp, size_t tmp_bytes, const unsigned long long *keys_i
     return 1 + (end_bit + 7) / 8;
 }
 
+// 7 bits per cell axis (cells repeat every 128 cells = 205 m at 0.8 m voxels: the reach of a 100 m scan) + 3 voxel bits = 24 key
+// bits = three 8-bit radix passes.  Aliasing cells only cost time (see the header comment).
+constexpr int kCellBits = 7;
+constexpr uint32_t kCellMask = (1u << kCellBits) - 1u;
+constexpr int kKeyBitsTile = 3 * kCellBits + 3;
 constexpr int kUnitQueries = 128;  // = kTileThreads of search_tile.cuh (checked in registration.cu)
 constexpr int kHeadTile = 1024;    // positions per block of the head count / compaction kernels
 
@@ -52,11 +57,11 @@ __global__ void tile_key_kernel(const double4 *__restrict__ frame, uint32_t n, P
     const double4 s = frame[i];
     double x = s.x, y = s.y, z = s.z;
     if (apply) pose_act(guess, s.x, s.y, s.z, x, y, z);
-    // cell = voxel >> 1 (arithmetic shift = floor), 9 bits per axis, then the voxel inside the cell: queries that share a home
+    // cell = voxel >> 1 (arithmetic shift = floor), kCellBits bits per axis, then the voxel inside the cell: queries that share a home
     // voxel are neighbours in the order, so a warp's home-bucket scan is converged
     const int vx = trunc_div(x, vs), vy = trunc_div(y, vs), vz = trunc_div(z, vs);
-    keys[i] = ((uint32_t)((vx >> 1) & 511) << 21) | ((uint32_t)((vy >> 1) & 511) << 12) | ((uint32_t)((vz >> 1) & 511) << 3) |
-              ((uint32_t)(vx & 1) << 2) | ((uint32_t)(vy & 1) << 1) | (uint32_t)(vz & 1);
+    keys[i] = ((uint32_t)((vx >> 1) & kCellMask) << (2 * kCellBits + 3)) | ((uint32_t)((vy >> 1) & kCellMask) << (kCellBits + 3)) |
+              ((uint32_t)((vz >> 1) & kCellMask) << 3) | ((uint32_t)(vx & 1) << 2) | ((uint32_t)(vy & 1) << 1) | (uint32_t)(vz & 1);
     vals[i] = i;
 }
 
@@ -72,14 +77,14 @@ __global__ void tile_heads_kernel(const uint32_t *__restrict__ keys, uint32_t n,
     if (j0 >= n) return;
     const uint32_t j1 = j0 + kUnitQueries < n ? j0 + kUnitQueries : n;
     uint32_t prev = keys[j0] >> 3;
-    int lx = (int)(prev >> 18), ly = (int)((prev >> 9) & 511u), lz = (int)(prev & 511u), hx = lx, hy = ly, hz = lz;
+    int lx = (int)(prev >> (2 * kCellBits)), ly = (int)((prev >> kCellBits) & kCellMask), lz = (int)(prev & kCellMask), hx = lx, hy = ly, hz = lz;
     head[j0] = 1;
     for (uint32_t j = j0 + 1; j < j1; ++j) {
         const uint32_t cell = keys[j] >> 3;
         uint8_t h = 0;
         if (cell != prev) {
             prev = cell;
-            const int x = (int)(cell >> 18), y = (int)((cell >> 9) & 511u), z = (int)(cell & 511u);
+            const int x = (int)(cell >> (2 * kCellBits)), y = (int)((cell >> kCellBits) & kCellMask), z = (int)(cell & kCellMask);
             const int nlx = min(lx, x), nhx = max(hx, x), nly = min(ly, y), nhy = max(hy, y), nlz = min(lz, z), nhz = max(hz, z);
             if ((2 * (nhx - nlx) + 4) * (2 * (nhy - nly) + 4) * (2 * (nhz - nlz) + 4) > kMergeSlots) {
                 h = 1;
@@ -174,11 +179,11 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
     tile_group_cnt_.ensure(groups);
     SAGE_CUDA(cudaMemsetAsync(tile_group_cnt_.p, 0, groups * sizeof(uint32_t), stream_));
     if ((size_t)17 * groups > partials_.cap) partials_.ensure((size_t)17 * groups);
-    const size_t tmp_bytes = sort_pairs_tmp_bytes_u32(n, 30);
+    const size_t tmp_bytes = sort_pairs_tmp_bytes_u32(n, kKeyBitsTile);
     tile_tmp_.ensure(tmp_bytes ? tmp_bytes : 1);
     SAGE_LAUNCH(tile_key_kernel, (n32 + 255) / 256, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, voxel_size_, tile_keys_[0].p,
                 tile_vals_[0].p);
-    g_launches.fetch_add(sort_pairs_u32(tile_tmp_.p, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, n, 30, stream_),
+    g_launches.fetch_add(sort_pairs_u32(tile_tmp_.p, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, n, kKeyBitsTile, stream_),
                          std::memory_order_relaxed);
     tile_flag_.ensure(n);
     const uint32_t chunks = (n32 + kUnitQueries - 1) / kUnitQueries;

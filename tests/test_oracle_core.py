@@ -226,3 +226,28 @@ def test_deskew_matches_numpy(orc):
     for i in range(300):
         assert np.allclose(out[i, :3], orc.se3_act(orc.se3_exp((ts[i] - 0.5) * delta), frame[i, :3]), atol=1e-13)
     assert np.array_equal(out[:, 3], frame[:, 3])
+
+
+def test_key_frame_grid_and_overlap_against_numpy(orc):
+    """utils::EigenToGridMap / compute_occ_overlap (ros/ros2/Utils.hpp:220-258) restated in the oracle vs a numpy restatement:
+    inclusive bounds, the upper bound added before the division, truncation toward zero, cells set to 1; overlap = |s & t| / |s|."""
+    rng = np.random.default_rng(3)
+    bounds = [[-51.2, 51.2], [-51.2, 51.2], [-4.0, 2.4]]  # ros/launch/odometry.launch.py:88
+    H, W = 128, 128                                        # :90
+    pts = np.c_[rng.uniform(-60, 60, (20000, 2)), rng.uniform(-6, 4, 20000), rng.integers(0, 100, 20000)].astype(float)
+    pts[:50, 0] = 51.2    # on the inclusive upper bound: index W -> rejected by the range check
+    pts[50:100, 1] = -51.2
+    g = orc.grid_map(pts, bounds, H, W)
+    ref = np.zeros((H, W), np.int32)
+    xr, yr = (bounds[0][1] - bounds[0][0]) / W, (bounds[1][1] - bounds[1][0]) / H
+    for x, y, z, _ in pts:
+        if x < bounds[0][0] or x > bounds[0][1] or y < bounds[1][0] or y > bounds[1][1] or z < bounds[2][0] or z > bounds[2][1]:
+            continue
+        ox, oy = int((x + bounds[0][1]) / xr), int((y + bounds[1][1]) / yr)
+        if 0 <= ox < W and 0 <= oy < H:
+            ref[oy, ox] = 1
+    assert np.array_equal(g, ref) and 0 < g.sum() < H * W
+    g2 = orc.grid_map(pts[::2] + [0.7, -0.3, 0, 0], bounds, H, W)
+    assert orc.occ_overlap(g, g2) == pytest.approx((g & g2).sum() / g.sum())
+    assert orc.occ_overlap(g, g) == 1.0
+    assert np.isnan(orc.occ_overlap(np.zeros_like(g), g))  # 0 / 0, as the reference

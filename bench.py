@@ -348,7 +348,9 @@ def hbm_regime_leg(sg, torch, device: int, map_points: int, base_pts: np.ndarray
     iters, launches, ms = m.profile_read_launches()
     m.profile_enable(False)
     us = 1e3 * ms / max(1, iters)
-    requested = 16.0 * (work[4] + work[1]) + 96.0 * len(q)  # staged records + table probes + query in/out + winner record
+    # records the kernel pulls (staged by TMA in the tile search, else ranked straight from global memory) + table probes + query
+    # in/out + winner record
+    requested = 16.0 * ((work[4] if work[4] > 0 else work[0]) + work[1]) + 96.0 * len(q)
     out = {"workload": f"120k queries uniform over a {m.num_points()}-pt / {m.num_voxels()}-voxel map ({tiles} copies of the bench map along x), "
                        f"{ITERS} GN iterations, L2 flushed between registrations",
            "bound": "hbm", "algorithmic_bytes_per_iteration": alg, "us_per_iteration": us, "achieved": alg / us / 1e3, "peak": peak,

@@ -112,6 +112,33 @@ size_t orc_robin_order(const int32_t *keys, size_t n, int64_t *order_out) {
     return t.bucket_count();
 }
 
+// General replay for the third-party self-check (tools/verify_thirdparty.cpp): ops[i] = {kind, x, y, z}; kind 0 = insert(key) if
+// absent, 1 = erase(key) if present, 2 = the reference's erase-while-iterating sweep (core/VoxelHashMap.cpp:176-184) erasing
+// every key with x < ops[i].x that the iterator meets.  Writes the final iteration order (the id each key got at its insertion:
+// its op index); returns its length.
+size_t orc_robin_replay(const int32_t *ops, size_t n_ops, int64_t *order_out, int64_t *bucket_count_out) {
+    RobinTable<int64_t> t;
+    for (size_t i = 0; i < n_ops; ++i) {
+        const int32_t *o = ops + 4 * i;
+        const Voxel k{o[1], o[2], o[3]};
+        if (o[0] == 0) {
+            if (!t.contains(k)) t.insert(k, (int64_t)i);
+        } else if (o[0] == 1) {
+            const size_t ib = t.find(k);
+            if (ib != t.npos) t.erase_at(ib);
+        } else {
+            auto &B = t.buckets();
+            for (size_t ib = 0; ib < B.size(); ++ib)
+                if (!B[ib].empty() && B[ib].key.x < o[1]) t.erase_at(ib);
+        }
+    }
+    size_t k = 0;
+    for (const auto &b : t.buckets())
+        if (!b.empty()) order_out[k++] = b.value;
+    if (bucket_count_out) *bucket_count_out = (int64_t)t.bucket_count();
+    return k;
+}
+
 // ---- core free functions -------------------------------------------------------------------
 size_t orc_preprocess(const double *xyzl, size_t n, double max_range, double min_range, double label_max_range,
                       double *out, size_t cap) {

@@ -42,7 +42,7 @@ def lib() -> C.CDLL:
         L.orc_pipeline_map.restype = C.c_void_p
         for f in ("orc_preprocess", "orc_preprocess_dynamic", "orc_preprocess_dynamic_ordered", "orc_voxel_downsample", "orc_map_num_voxels", "orc_map_bucket_count", "orc_map_num_points",
                   "orc_map_pointcloud", "orc_map_dump", "orc_map_get_correspondences", "orc_last_source",
-                  "orc_last_frame_downsample", "orc_num_poses", "orc_local_map", "orc_robin_order", "orc_voxelize", "orc_deskew"):
+                  "orc_last_frame_downsample", "orc_num_poses", "orc_local_map", "orc_robin_order", "orc_robin_replay", "orc_voxelize", "orc_deskew"):
             getattr(L, f).restype = C.c_size_t
         for f in ("orc_get_adaptive_threshold", "orc_last_sigma", "orc_rotation_angle", "orc_occ_overlap"):
             getattr(L, f).restype = C.c_double
@@ -107,6 +107,14 @@ def robin_order(keys: np.ndarray) -> Tuple[np.ndarray, int]:
 
 
 # ---- core free functions ---------------------------------------------------------------------
+def robin_replay(ops: np.ndarray) -> Tuple[np.ndarray, int]:
+    """ops (n, 4) int32 = kind (0 insert, 1 erase, 2 sweep-erase keys with x < ops.x while iterating), x, y, z.
+    Returns (final iteration order as the op indices that inserted the surviving keys, bucket_count)."""
+    ops = np.ascontiguousarray(ops, np.int32); order = np.empty(len(ops), np.int64); bc = C.c_int64()
+    n = lib().orc_robin_replay(ops.ctypes.data_as(_ip), C.c_size_t(len(ops)), order.ctypes.data_as(_lp), C.byref(bc))
+    return order[:n].copy(), int(bc.value)
+
+
 def preprocess(pts, max_range, min_range, label_max_range) -> np.ndarray:
     pts = _c64(pts); out = np.empty_like(pts)
     n = lib().orc_preprocess(_d(pts), C.c_size_t(len(pts)), C.c_double(max_range), C.c_double(min_range),

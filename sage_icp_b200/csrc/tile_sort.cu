@@ -2,8 +2,8 @@
 // the ordered array into units for the tile search (search_tile.cuh).  The order is a locality hint only: the tile kernel
 // recomputes every unit's region from the queries' actual voxels each iteration, so a poor order costs time, never correctness.
 //
-//   tile_key_kernel     key = low 7 bits of each cell coordinate + the voxel inside the cell (cells repeat every 128 cells = 205 m
-//                       at 0.8 m voxels; two aliasing cells in one run merely make a unit whose region does not fit, which falls
+//   tile_key_kernel     key = low 8 / 8 / 5 bits of the cell coordinates + the voxel inside the cell (cells repeat every 410 m
+//                       horizontally, 51 m vertically at 0.8 m voxels; two aliasing cells in one run merely make a unit whose region does not fit, which falls
 //                       back to global search)
 //   cub::DeviceRadixSort::SortPairs over the 30 key bits (stable, deterministic: equal inputs give equal unit lists, which is
 //                       what makes the sums reproducible run to run)
@@ -42,11 +42,12 @@ int sort_pairs_u64(void *tmp, size_t tmp_bytes, const unsigned long long *keys_i
     return 1 + (end_bit + 7) / 8;
 }
 
-// 7 bits per cell axis (cells repeat every 128 cells = 205 m at 0.8 m voxels: the reach of a 100 m scan) + 3 voxel bits = 24 key
-// bits = three 8-bit radix passes.  Aliasing cells only cost time (see the header comment).
-constexpr int kCellBits = 7;
-constexpr uint32_t kCellMask = (1u << kCellBits) - 1u;
-constexpr int kKeyBitsTile = 3 * kCellBits + 3;
+// 8 bits for the horizontal cell axes (cells repeat every 256 cells = 410 m at 0.8 m voxels: twice the reach of a 100 m scan), 5 for
+// the vertical one (51 m) + 3 voxel bits = 24 key bits = three 8-bit radix passes.  Cells that alias get the same key and may
+// share a unit whose region then does not fit: that costs time (global-memory fallback of that unit), never correctness.
+constexpr int kCellBitsXY = 8, kCellBitsZ = 5;
+constexpr uint32_t kCellMaskXY = (1u << kCellBitsXY) - 1u, kCellMaskZ = (1u << kCellBitsZ) - 1u;
+constexpr int kKeyBitsTile = 2 * kCellBitsXY + kCellBitsZ + 3;
 constexpr int kUnitQueries = 128;  // = kTileThreads of search_tile.cuh (checked in registration.cu)
 constexpr int kHeadTile = 1024;    // positions per block of the head count / compaction kernels
 
@@ -57,43 +58,53 @@ __global__ void tile_key_kernel(const double4 *__restrict__ frame, uint32_t n, P
     const double4 s = frame[i];
     double x = s.x, y = s.y, z = s.z;
     if (apply) pose_act(guess, s.x, s.y, s.z, x, y, z);
-    // cell = voxel >> 1 (arithmetic shift = floor), kCellBits bits per axis, then the voxel inside the cell: queries that share a home
+    // cell = voxel >> 1 (arithmetic shift = floor), 8 + 8 + 5 bits, then the voxel inside the cell: queries that share a home
     // voxel are neighbours in the order, so a warp's home-bucket scan is converged
     const int vx = trunc_div(x, vs), vy = trunc_div(y, vs), vz = trunc_div(z, vs);
-    keys[i] = ((uint32_t)((vx >> 1) & kCellMask) << (2 * kCellBits + 3)) | ((uint32_t)((vy >> 1) & kCellMask) << (kCellBits + 3)) |
-              ((uint32_t)((vz >> 1) & kCellMask) << 3) | ((uint32_t)(vx & 1) << 2) | ((uint32_t)(vy & 1) << 1) | (uint32_t)(vz & 1);
+    keys[i] = ((uint32_t)((vx >> 1) & kCellMaskXY) << (kCellBitsXY + kCellBitsZ + 3)) | ((uint32_t)((vy >> 1) & kCellMaskXY) << (kCellBitsZ + 3)) |
+              ((uint32_t)((vz >> 1) & kCellMaskZ) << 3) | ((uint32_t)(vx & 1) << 2) | ((uint32_t)(vy & 1) << 1) | (uint32_t)(vz & 1);
     vals[i] = i;
 }
 
-// Unit boundaries.  One thread walks one aligned chunk of kUnitQueries sorted positions: a unit starts at the chunk start and
+// Unit boundaries.  One warp walks one aligned chunk of kUnitQueries sorted positions: a unit starts at the chunk start and
 // wherever taking in the next cell would make the unit's region — the bounding box of its cells, in voxels, grown by one voxel
 // on every side — larger than kMergeSlots.  Dense chunks (one to three cells) stay one full unit; sparse ones (a cell every few
 // queries) are cut where their cells stop being neighbours.  kMergeSlots leaves room for the queries to drift by a voxel per axis
 // during the Gauss-Newton iterations before a region outgrows the tile kernel's table (kTileSlots = 256).
 constexpr int kMergeSlots = 144;
 __global__ void tile_heads_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint8_t *__restrict__ head) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per chunk: the lanes load 32 consecutive keys at a time and find the cell changes; the walk over those (few)
+    // changes is done redundantly by every lane (it is scalar work: a running bounding box)
+    const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const uint32_t j0 = c * kUnitQueries;
     if (j0 >= n) return;
-    const uint32_t j1 = j0 + kUnitQueries < n ? j0 + kUnitQueries : n;
-    uint32_t prev = keys[j0] >> 3;
-    int lx = (int)(prev >> (2 * kCellBits)), ly = (int)((prev >> kCellBits) & kCellMask), lz = (int)(prev & kCellMask), hx = lx, hy = ly, hz = lz;
-    head[j0] = 1;
-    for (uint32_t j = j0 + 1; j < j1; ++j) {
-        const uint32_t cell = keys[j] >> 3;
-        uint8_t h = 0;
-        if (cell != prev) {
-            prev = cell;
-            const int x = (int)(cell >> (2 * kCellBits)), y = (int)((cell >> kCellBits) & kCellMask), z = (int)(cell & kCellMask);
+    int lx = 0, ly = 0, lz = 0, hx = 0, hy = 0, hz = 0;
+    uint32_t prev_cell = 0;
+    for (uint32_t r = 0; r < kUnitQueries / 32; ++r) {
+        const uint32_t j = j0 + 32 * r + lane;
+        const bool in = j < n;
+        const uint32_t cell = in ? keys[j] >> 3 : 0u;
+        uint32_t before = __shfl_up_sync(0xffffffffu, cell, 1);
+        if (lane == 0) before = prev_cell;
+        const bool first = r == 0 && lane == 0;
+        unsigned changes = __ballot_sync(0xffffffffu, in && (first || cell != before));
+        unsigned cuts = 0;
+        while (changes) {
+            const int b = __ffs(changes) - 1;
+            changes &= changes - 1;
+            const uint32_t cb = __shfl_sync(0xffffffffu, cell, b);
+            const int x = (int)(cb >> (kCellBitsXY + kCellBitsZ)), y = (int)((cb >> kCellBitsZ) & kCellMaskXY), z = (int)(cb & kCellMaskZ);
             const int nlx = min(lx, x), nhx = max(hx, x), nly = min(ly, y), nhy = max(hy, y), nlz = min(lz, z), nhz = max(hz, z);
-            if ((2 * (nhx - nlx) + 4) * (2 * (nhy - nly) + 4) * (2 * (nhz - nlz) + 4) > kMergeSlots) {
-                h = 1;
+            if ((r == 0 && b == 0) || (2 * (nhx - nlx) + 4) * (2 * (nhy - nly) + 4) * (2 * (nhz - nlz) + 4) > kMergeSlots) {
+                cuts |= 1u << b;  // the chunk start, or a cell that does not fit the unit's region any more
                 lx = hx = x, ly = hy = y, lz = hz = z;
             } else {
                 lx = nlx, hx = nhx, ly = nly, hy = nhy, lz = nlz, hz = nhz;
             }
         }
-        head[j] = h;
+        if (in) head[j] = (uint8_t)((cuts >> lane) & 1u);
+        prev_cell = __shfl_sync(0xffffffffu, cell, 31);
     }
 }
 
@@ -187,7 +198,7 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
                          std::memory_order_relaxed);
     tile_flag_.ensure(n);
     const uint32_t chunks = (n32 + kUnitQueries - 1) / kUnitQueries;
-    SAGE_LAUNCH(tile_heads_kernel, (chunks + 127) / 128, 128, 0, stream_, tile_keys_[1].p, n32, tile_flag_.p);
+    SAGE_LAUNCH(tile_heads_kernel, (chunks + 7) / 8, 256, 0, stream_, tile_keys_[1].p, n32, tile_flag_.p);  // one warp per chunk
     SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, tile_flag_.p, tile_vals_[1].p, src_.p,
                 tile_heads_.p);
     SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_flag_.p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);

@@ -86,21 +86,21 @@ def test_tile_registration_equals_legacy_and_is_reproducible(orc, monkeypatch):
 
 
 def test_tile_units_that_do_not_fit_fall_back_to_the_global_search(orc, monkeypatch):
-    """Cells 128 cells (204.8 m) apart share a sort key: queries of both land in one unit whose region cannot fit, and the
+    """Cells 256 cells (409.6 m) apart share a sort key: queries of both land in one unit whose region cannot fit, and the
     unit is searched from global memory.  Scattered queries (one per cell) and a scene across voxel 0 ride along."""
     rng = np.random.default_rng(5)
     a = np.c_[rng.uniform(-6, 6, (60_000, 3)), rng.choice([0, 40, 50, 81], 60_000)]
     b = a.copy()
-    b[:, 0] += 204.8
-    b[:, 1] -= 2 * 204.8
+    b[:, 0] += 409.6
+    b[:, 1] -= 2 * 409.6
     pts = np.concatenate([a, b])
     g = _maps(orc, pts, monkeypatch, {"SAGE_TILE_MIN": "1"})
     o = orc.OracleMap(0.8, 1e9, 20, 20, BASIC_LABELS, evict_faithful=False)
     o.add_points(pts)
     qa = np.c_[rng.uniform(-7, 7, (9000, 3)), rng.choice([0, 40, 50, 81, 10], 9000)]
     qb = qa.copy()
-    qb[:, 0] += 204.8
-    qb[:, 1] -= 2 * 204.8
+    qb[:, 0] += 409.6
+    qb[:, 1] -= 2 * 409.6
     q = np.concatenate([qa, qb, np.c_[rng.uniform(-400, 400, (2000, 3)), np.zeros(2000)]])
     q = q[rng.permutation(len(q))]
     assert _check_corr(g, o, q, 2.0, 0.4) > 10000

@@ -190,6 +190,12 @@ public:
     // Extension (not in the reference): true = reproduce the reference map's tsl::robin_map behaviour — the far voxels its
     // erase-while-iterating sweep skips (core/VoxelHashMap.cpp:176-184) and LocalMap() in its iteration order.  Call right after
     // construction or reinitialize() (the map must be empty).  Costs a few host round trips per frame.
+    // Extension (not in the reference, which is CPU only): run this object on the given CUDA devices.  One id: that GPU.  Several:
+    // the ICP queries of every RegisterFrame are sharded over them (replicated map, sums all-reduced inside the search kernel over
+    // NVLink peer memory) — the one line a node adds after constructing sageICP to use a multi-GPU box.  Fresh object only.
+    void SetDevices(const std::vector<int> &cuda_devices) {
+        Check(sage_set_devices(Handle(), cuda_devices.data(), static_cast<int>(cuda_devices.size())));
+    }
     void SetReferenceMapSemantics(bool on) { Check(sage_map_set_eviction(sage_pipeline_map(Handle()), on ? 1 : 0)); }
 
 private:

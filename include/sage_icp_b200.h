@@ -67,10 +67,16 @@ sage_pipeline *sage_create(const sage_config_pod *config, int device);
 void sage_destroy(sage_pipeline *h);
 /* sageICP::reinitialize() — pipeline/sageICP.hpp:94-99 */
 int sage_reset(sage_pipeline *h);
-/* Move a fresh (or just reinitialised) pipeline to another GPU: ids[0] = CUDA ordinal, n must be 1 — a handle runs on one GPU;
- * several GPUs are used as one process per GPU over the core-level sage_map_comm_* entry points below.
- * The reference has no counterpart (CPU only); this is the device selection of its drop-in. */
+/* Device selection of the drop-in (the reference is CPU only).  Only on a fresh or reinitialised pipeline.
+ *   n == 1: the pipeline runs on GPU ids[0].
+ *   n >  1: ONE process, n GPUs of one node (peer access required).  The front end runs on ids[0]; every GPU holds a replica of the
+ *           map; RegisterFrame cuts its ICP queries into n contiguous slices, registers them concurrently with the 17
+ *           normal-equation sums all-reduced inside the search kernel over NVLink peer memory, checks that every GPU returned the
+ *           same pose, and applies the same map update on every replica.  Poses equal the single-GPU ones to rounding (other
+ *           summation order).  Changes made through sage_pipeline_map() (loads, eviction mode) reach the first GPU only: set them
+ *           before this call.  The ROS node uses several GPUs with this one line after constructing sageICP. */
 int sage_set_devices(sage_pipeline *h, const int *ids, int n);
+int sage_num_devices(sage_pipeline *h);
 
 /* sageICP::RegisterFrame(frame[, timestamps]) — pipeline/sageICP.cpp:36-52 and :54-95.
  * xyzl: HOST pointer, n x 4 doubles.  timestamps: NULL or n doubles (used only when config.deskew).

@@ -323,9 +323,13 @@ class SagePipeline:
     def reinitialize(self): self._chk(self.L.sage_reset(self.h), "sage_reset")
 
     def set_devices(self, ids):
-        """Move a fresh pipeline to GPU ids[0] (exactly one id: a handle runs on one GPU)."""
+        """A fresh pipeline on GPU ids[0]; with several ids, one replica of the map per GPU and every frame's ICP queries sharded
+        over all of them (one process, peer-memory all-reduce inside the search kernel)."""
         a = (C.c_int * len(ids))(*ids)
         self._chk(self.L.sage_set_devices(self.h, a, len(ids)), "sage_set_devices")
+
+    def num_devices(self) -> int:
+        return int(self._chk(self.L.sage_num_devices(self.h), "sage_num_devices"))
 
     def register_frame(self, pts, timestamps=None):
         """RegisterFrame(frame[, timestamps]) -> (pose7, t_icp, t_all); `source` via last_source()."""

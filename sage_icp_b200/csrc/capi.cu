@@ -132,20 +132,26 @@ int sage_set_devices(sage_pipeline *h, const int *ids, int n) {
     return (int)guarded([&] {
         P(h);
         need(ids, "ids");
-        if (n != 1)
-            throw ArgError("a handle runs on one GPU: use one process per GPU and sage_map_comm_peer_attach / sage_map_comm_init to shard a "
-                           "registration over several");
-        if (ids[0] == h->device) return 0;
-        if (!h->impl->poses().empty() || !h->impl->map().empty()) throw ArgError("the device can only be changed on a fresh or reinitialised pipeline");
-        std::unique_ptr<Pipeline> p(new Pipeline(h->config->pod, ids[0]));  // throws if the device is unusable; the old one stays
-        const bool faithful = h->impl->map().eviction_faithful();
-        p->map().set_eviction_faithful(faithful);
-        delete h->impl;
-        h->impl = p.release();
-        h->map_handle = sage_map{&h->impl->map(), false};
-        h->device = ids[0];
+        if (n < 1 || n > 8) throw ArgError("sage_set_devices: 1..8 GPUs of one node");
+        if (!h->impl->poses().empty() || !h->impl->map().empty()) {
+            if (n == 1 && ids[0] == h->device && h->impl->n_devices() == 1) return 0;
+            throw ArgError("the devices can only be changed on a fresh or reinitialised pipeline");
+        }
+        if (ids[0] != h->device) {
+            std::unique_ptr<Pipeline> p(new Pipeline(h->config->pod, ids[0]));  // throws if the device is unusable; the old one stays
+            p->map().set_eviction_faithful(h->impl->map().eviction_faithful());
+            delete h->impl;
+            h->impl = p.release();
+            h->map_handle = sage_map{&h->impl->map(), false};
+            h->device = ids[0];
+        }
+        // n > 1: one replica of the map per extra GPU; RegisterFrame shards its ICP queries over all of them
+        h->impl->set_replica_devices(std::vector<int>(ids + 1, ids + n));
         return 0;
     });
+}
+int sage_num_devices(sage_pipeline *h) {
+    return (int)guarded([&] { return (long long)P(h).n_devices(); });
 }
 int sage_reset(sage_pipeline *h) {
     return (int)guarded([&] {

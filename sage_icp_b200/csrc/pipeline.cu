@@ -5,6 +5,9 @@
 #include "pipeline.cuh"
 
 #include <chrono>
+#include <cstring>
+#include <exception>
+#include <thread>
 
 namespace sage {
 
@@ -48,6 +51,7 @@ Pipeline::Pipeline(const sage_config_pod &c, int device)
         for (int k = 0; k < c.n_dynamic_remove_lankmark; ++k) dyn_.landmark_labels[k] = c.dynamic_remove_lankmark[k];
         dyn_.dy_th = c.dynamic_vehicle_filter_th;
     }
+    basic_labels_.assign(c.basic_parts_labels, c.basic_parts_labels + c.n_basic_parts_labels);
     // own copies of the label arrays (the POD's pointers belong to the caller)
     cfg_.group_offsets = cfg_.group_labels = cfg_.basic_parts_labels = cfg_.dynamic_remove_lankmark = nullptr;
     cfg_.voxel_size = nullptr;
@@ -78,6 +82,86 @@ void Pipeline::reinitialize() {  // pipeline/sageICP.hpp:94-99
     poses_.clear();
     reset_threshold();
     map_.clear();
+    for (auto &r : replicas_) r->map->clear();
+}
+
+void Pipeline::set_replica_devices(const std::vector<int> &devices) {
+    if (!poses_.empty() || !map_.empty()) throw ArgError("the devices can only be changed on a fresh or reinitialised pipeline");
+    if (devices.size() + 1 > 8) throw ArgError("at most 8 GPUs of one node");
+    for (size_t i = 0; i < devices.size(); ++i) {
+        if (devices[i] == map_.device()) throw ArgError("sage_set_devices: a GPU is listed twice");
+        for (size_t j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) throw ArgError("sage_set_devices: a GPU is listed twice");
+    }
+    map_.peer_detach();
+    replicas_.clear();
+    if (devices.empty()) return;
+    for (int d : devices) {
+        std::unique_ptr<Replica> r(new Replica);
+        r->device = d;
+        r->map.reset(new VoxelMapGPU(cfg_.voxel_size_map, cfg_.local_map_range, cfg_.basic_points_per_voxel, cfg_.critical_points_per_voxel,
+                                     basic_labels_.data(), (int)basic_labels_.size(), d));
+        r->map->set_eviction_faithful(map_.eviction_faithful());
+        replicas_.push_back(std::move(r));
+    }
+    const int world = (int)replicas_.size() + 1;
+    double *bufs[8];
+    int devs[8];
+    bufs[0] = map_.peer_local_buffer(), devs[0] = map_.device();
+    for (int k = 1; k < world; ++k) bufs[k] = replicas_[k - 1]->map->peer_local_buffer(), devs[k] = replicas_[k - 1]->device;
+    map_.peer_attach_local(0, world, bufs, devs);
+    for (int k = 1; k < world; ++k) replicas_[k - 1]->map->peer_attach_local(k, world, bufs, devs);
+}
+
+// sage_icp::RegisterFrame + VoxelHashMap::Update on every GPU of the handle.  Rank r registers the contiguous query slice
+// [n r / R, n (r + 1) / R) against its own replica of the map; the sums meet inside the search kernel, so every rank takes the same
+// steps and returns the same pose, bit for bit; then every rank applies the same update to its replica.
+int Pipeline::register_sharded(const Pose &guess, double max_dist, double kernel, Pose &pose_out) {
+    const int world = (int)replicas_.size() + 1;
+    SAGE_CUDA(cudaSetDevice(map_.device()));
+    SAGE_CUDA(cudaStreamSynchronize(map_.stream()));  // ds_ / src_ are complete before the other GPUs read them
+    std::vector<Pose> poses((size_t)world);
+    std::vector<int> iters((size_t)world, 0);
+    std::vector<std::exception_ptr> errors((size_t)world);
+    auto slice = [&](int r, size_t &lo, size_t &cnt) {
+        lo = n_src_ * (size_t)r / (size_t)world;
+        cnt = n_src_ * (size_t)(r + 1) / (size_t)world - lo;
+    };
+    auto work = [&](int r) {
+        try {
+            Replica &rep = *replicas_[(size_t)r - 1];
+            SAGE_CUDA(cudaSetDevice(rep.device));
+            size_t lo, cnt;
+            slice(r, lo, cnt);
+            rep.src.ensure(cnt ? cnt : 1);
+            rep.ds.ensure(n_ds_ ? n_ds_ : 1);
+            cudaStream_t st = rep.map->stream();
+            if (cnt) SAGE_CUDA(cudaMemcpyPeerAsync(rep.src.p, rep.device, src_.p + lo, map_.device(), cnt * sizeof(double4), st));
+            if (n_ds_) SAGE_CUDA(cudaMemcpyPeerAsync(rep.ds.p, rep.device, ds_.p, map_.device(), n_ds_ * sizeof(double4), st));
+            iters[(size_t)r] = rep.map->register_frame_dev(rep.src.p, cnt, guess, max_dist, kernel, cfg_.sem_th, 500, 1e-4, poses[(size_t)r]);
+            rep.map->update_dev(rep.ds.p, n_ds_, poses[(size_t)r]);
+        } catch (...) {
+            errors[(size_t)r] = std::current_exception();
+        }
+    };
+    std::vector<std::thread> threads;
+    for (int r = 1; r < world; ++r) threads.emplace_back(work, r);
+    try {
+        size_t lo, cnt;
+        slice(0, lo, cnt);
+        iters[0] = map_.register_frame_dev(src_.p, cnt, guess, max_dist, kernel, cfg_.sem_th, 500, 1e-4, poses[0]);
+    } catch (...) {
+        errors[0] = std::current_exception();
+    }
+    for (auto &t : threads) t.join();
+    SAGE_CUDA(cudaSetDevice(map_.device()));
+    for (auto &e : errors)
+        if (e) std::rethrow_exception(e);
+    for (int r = 1; r < world; ++r)
+        if (std::memcmp(&poses[(size_t)r], &poses[0], sizeof(Pose)) != 0 || iters[(size_t)r] != iters[0])
+            throw CudaError("sharded registration: the GPUs disagree on the pose (replicated maps out of step?)");
+    pose_out = poses[0];
+    return iters[0];
 }
 
 // AdaptiveThreshold::ComputeThreshold — core/Threshold.cpp:39-50
@@ -181,7 +265,10 @@ void Pipeline::register_frame_dev(const double4 *raw, size_t n, const double *ti
     const Pose initial_guess = pose_mul(last_pose, prediction);
     const auto t1 = clock::now();
     Pose new_pose;
-    last_iters_ = map_.register_frame_dev(src_.p, n_src_, initial_guess, 3.0 * sigma, sigma / 3.0, cfg_.sem_th, 500, 1e-4, new_pose);
+    if (replicas_.empty())
+        last_iters_ = map_.register_frame_dev(src_.p, n_src_, initial_guess, 3.0 * sigma, sigma / 3.0, cfg_.sem_th, 500, 1e-4, new_pose);
+    else
+        last_iters_ = register_sharded(initial_guess, 3.0 * sigma, sigma / 3.0, new_pose);  // the replicas also update their maps
     const auto t2 = clock::now();
     model_deviation_ = pose_mul(pose_inverse(initial_guess), new_pose);
     map_.update_dev(ds_.p, n_ds_, new_pose);  // asynchronous: overlaps the caller and the next frame's upload

@@ -1,5 +1,6 @@
 // Host-side mirror of sage_icp::pipeline::sageICP (pipeline/sageICP.hpp:67-109) over the device kernels.
 #pragma once
+#include <memory>
 #include <vector>
 
 #include "../../include/sage_icp_b200.h"
@@ -22,6 +23,12 @@ public:
     bool has_moved();
     Pose get_prediction_model() const;
     void reinitialize();
+    // sage_set_devices with n > 1: this process drives one map replica per extra GPU.  The front end runs on the first device;
+    // the ICP queries are cut into contiguous shards, one per GPU, registered concurrently (one host thread per replica) with the
+    // 17 sums all-reduced inside the search kernel over peer memory; every replica applies the same map update.  Only on a fresh
+    // or reinitialised pipeline.
+    void set_replica_devices(const std::vector<int> &devices);
+    size_t n_devices() const { return replicas_.size() + 1; }
     long long preprocess_host(const double *xyzl, size_t n, std::vector<double> &out);
     long long downsample_host(const double *xyzl, size_t n, double scale, std::vector<double> &out);
 
@@ -48,6 +55,15 @@ private:
     CropParams crop() const;
     size_t preprocess_dev(const double4 *raw, size_t n, double4 *out);  // Preprocess, either branch
     DynFilterParams dyn_{};
+
+    struct Replica {
+        int device;
+        std::unique_ptr<VoxelMapGPU> map;
+        DevBuf<double4> src, ds;
+    };
+    std::vector<std::unique_ptr<Replica>> replicas_;
+    std::vector<int> basic_labels_;  // kept for building replicas
+    int register_sharded(const Pose &guess, double max_dist, double kernel, Pose &pose_out);  // ICP + map update on every GPU
 
     sage_config_pod cfg_;  // scalar fields only (array pointers nulled)
     VoxelMapGPU map_;

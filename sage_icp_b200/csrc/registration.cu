@@ -73,6 +73,9 @@ struct IterParams {
     // the capacity of the block's staging area in 16-byte records
     const uint32_t *tile_units, *tile_n_units, *tile_perm;  // tile_perm: sorted position -> index in the caller's array
     double *tile_unit_part;    // [unit][17]
+    uint32_t *tile_heavy_q;    // [2][tile_heavy_cap] heavy-first queues (iteration parity)
+    uint8_t *tile_heavy_flag;  // [2][tile_heavy_cap] 1 = the unit is on that iteration's queue
+    uint32_t tile_heavy_cap;
     uint32_t *tile_group_cnt;  // [group]
     uint32_t tile_stage_cap;
     unsigned long long *dbg;  // optional per-block timeline (tools/perf_probe.py): 4 globaltimer stamps per block + 4 global
@@ -245,6 +248,10 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->done = (max_iters <= 0);
     st->ticket = 0;
     st->unit_next = 0;
+    st->fetch_base = 0;
+    st->heavy_n[0] = st->heavy_n[1] = 0;
+    st->heavy_ns = 25000u;  // first guess: twice a typical unit
+    st->unit_ns_sum = 0;
     st->stat_occupied = st->stat_candidates = 0;
     st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = st->stat_staged = 0;
     st->comm_error = 0;
@@ -518,20 +525,35 @@ __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
     __threadfence();
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x] = gtime();
-    // the last block adds the per-block partials: warp w owns sums w, w+W, w+2W, ...; lane l adds blocks l, l+32, ... in order
-    // (four loads in flight), then a fixed butterfly — the same tree for a given grid, so results are reproducible
-    for (int k = warp; k < kSums; k += kWarps) {
-        const double *pk = p.partials + (size_t)k * count;
-        double v = 0;
-        uint32_t b = lane;
-        for (; b + 96 < count; b += 128) {
-            const double a0 = __ldcg(pk + b), a1 = __ldcg(pk + b + 32), a2 = __ldcg(pk + b + 64), a3 = __ldcg(pk + b + 96);
-            v += a0, v += a1, v += a2, v += a3;
-        }
-        for (; b < count; b += 32) v += __ldcg(pk + b);
+    // this block adds the partials: warp w owns sums w, w+W, w+2W, ...; lane l adds partials l, l+32, ... of each in order, then a
+    // fixed butterfly — the same tree for a given count, so results are reproducible.  The loads of all the sums a warp owns are
+    // issued together (one round trip per 32 partials instead of one per sum).
+    {
+        constexpr int kMaxOwn = (kSums + 1) / 2;  // >= ceil(kSums / kWarps) for kWarps >= 2 (blocks have at least 64 threads)
+        double v[kMaxOwn];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) st->sums[k] = v, s_sums[k] = v;
+        for (int i = 0; i < kMaxOwn; ++i) v[i] = 0.0;
+#pragma unroll 2
+        for (uint32_t b = lane; b < count; b += 32) {
+            double a[kMaxOwn];
+#pragma unroll
+            for (int i = 0; i < kMaxOwn; ++i) {
+                const int k = warp + kWarps * i;
+                a[i] = k < kSums ? __ldcg(p.partials + (size_t)k * count + b) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < kMaxOwn; ++i) v[i] += a[i];
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxOwn; ++i) {
+            const int k = warp + kWarps * i;
+            if (k < kSums) {  // warp-uniform
+                double t = v[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) st->sums[k] = t, s_sums[k] = t;
+            }
+        }
     }
     __syncthreads();
     if (p.xchg_world > 1) {
@@ -1052,6 +1074,7 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
     }
     p.tile_units = tile_units_.p, p.tile_n_units = tile_nunits_.p, p.tile_perm = tile_vals_[1].p, p.tile_stage_cap = tile_stage_cap_;
     p.tile_unit_part = tile_unit_part_.p, p.tile_group_cnt = tile_group_cnt_.p;
+    p.tile_heavy_q = tile_heavy_q_.p, p.tile_heavy_flag = tile_heavy_flag_.p, p.tile_heavy_cap = tile_heavy_cap_;
 }
 
 // mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points

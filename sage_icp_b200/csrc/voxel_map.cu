@@ -752,15 +752,46 @@ void VoxelMapGPU::peer_attach(int rank, int world, const uint8_t *handles) {
         SAGE_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         peer_buf_[k] = (double *)ptr;
     }
-    peer_rank_ = rank, peer_world_ = world, xchg_tag_ = 0;
+    peer_rank_ = rank, peer_world_ = world, xchg_tag_ = 0, peer_inprocess_ = false;
+}
+
+double *VoxelMapGPU::peer_local_buffer() {
+    set_device();
+    if (!xchg_local_) SAGE_CUDA(cudaMalloc(&xchg_local_, kXchgDoubles * sizeof(double)));
+    SAGE_CUDA(cudaStreamSynchronize(stream_));
+    SAGE_CUDA(cudaMemset(xchg_local_, 0, kXchgDoubles * sizeof(double)));
+    SAGE_CUDA(cudaDeviceSynchronize());
+    return xchg_local_;
+}
+
+void VoxelMapGPU::peer_attach_local(int rank, int world, double *const *buffers, const int *devices) {
+    set_device();
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) throw ArgError("peer_attach_local: 1..8 GPUs of one node");
+    if (buffers[rank] != xchg_local_ || !xchg_local_) throw ArgError("peer_attach_local: buffers[rank] must be this map's own buffer");
+    peer_detach();
+    for (int k = 0; k < world; ++k) {
+        if (k != rank) {
+            int can = 0;
+            SAGE_CUDA(cudaDeviceCanAccessPeer(&can, device_, devices[k]));
+            if (!can) throw CudaError("GPU " + std::to_string(device_) + " cannot access GPU " + std::to_string(devices[k]) + " (no peer path): the sharded registration needs NVLink/PCIe peer access");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[k], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled)
+                (void)cudaGetLastError();
+            else if (e != cudaSuccess)
+                throw CudaError(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        }
+        peer_buf_[k] = buffers[k];
+    }
+    peer_rank_ = rank, peer_world_ = world, xchg_tag_ = 0, peer_inprocess_ = true;
 }
 
 void VoxelMapGPU::peer_detach() {
     for (int k = 0; k < 8; ++k) {
-        if (peer_buf_[k] && peer_buf_[k] != xchg_local_) cudaIpcCloseMemHandle(peer_buf_[k]);
+        if (!peer_inprocess_ && peer_buf_[k] && peer_buf_[k] != xchg_local_) cudaIpcCloseMemHandle(peer_buf_[k]);
         peer_buf_[k] = nullptr;
     }
     peer_world_ = 0;
+    peer_inprocess_ = false;
 }
 
 void VoxelMapGPU::comm_destroy() {

@@ -112,6 +112,10 @@ public:
     void peer_handle(uint8_t out[64]);
     void peer_attach(int rank, int world, const uint8_t *handles);
     void peer_detach();
+    // the same exchange between several maps of ONE process (sage_set_devices with n > 1): the buffers are plain device pointers,
+    // reachable from every device once peer access is enabled — no IPC handles
+    double *peer_local_buffer();
+    void peer_attach_local(int rank, int world, double *const *buffers, const int *devices);
 
     // statistics mirror (refreshed by sync_stats)
     void sync_stats();
@@ -188,6 +192,9 @@ private:
     DevBuf<uint8_t> tile_tmp_, tile_flag_;  // sort scratch; unit-head flag per sorted position
     DevBuf<double> tile_unit_part_;      // [unit][17] sums of one unit
     DevBuf<uint32_t> tile_group_cnt_;    // units of a group that have published their sums
+    DevBuf<uint32_t> tile_heavy_q_;      // [2][cap] units to hand out first in the even / odd iterations (they were slow in the previous one)
+    DevBuf<uint8_t> tile_heavy_flag_;    // [2][cap]
+    uint32_t tile_heavy_cap_ = 0;
     int tile_grid_ = 0;            // co-resident blocks of the tile kernels
     int tile_minb_ = 6;            // which instantiation: 6 (80 registers) or 4 (128 registers) resident blocks per SM aimed at
     size_t tile_min_ = 0;          // scans of at least this many queries take the tile search (0 = never)
@@ -211,6 +218,7 @@ private:
     double *peer_buf_[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [rank] -> mapped exchange buffer
     double *xchg_local_ = nullptr;
     int peer_rank_ = 0, peer_world_ = 0;
+    bool peer_inprocess_ = false;  // peer_buf_ are other maps' buffers of this process (nothing to close on detach)
     unsigned long long xchg_tag_ = 0;                       // exchanges completed (same on every rank)
     unsigned long long xchg_timeout_ns_ = 30000000000ull;  // SAGE_XCHG_TIMEOUT_S
 };

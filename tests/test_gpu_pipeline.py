@@ -99,15 +99,18 @@ def test_reinitialize(orc, cfg):
 
 
 def test_set_devices(orc, cfg):
-    """sage_set_devices: one id per handle; a no-op for the current device; refused once the pipeline holds state; moving a
-    fresh pipeline to another GPU (when the box has one) gives the same poses."""
+    """sage_set_devices: a no-op for the current device; refused for unusable or repeated GPUs and once the pipeline holds state;
+    moving a fresh pipeline to another GPU (when the box has one) gives the same poses."""
     import sage_icp_b200 as sg
     gp = sg.SagePipeline(cfg)
     gp.set_devices([0])
-    with pytest.raises(sg.SageError, match="one GPU"):
-        gp.set_devices([0, 1])
+    assert gp.num_devices() == 1
+    with pytest.raises(sg.SageError, match="twice"):
+        gp.set_devices([0, 0])
     with pytest.raises(sg.SageError):
         gp.set_devices([sg.device_count()])  # no such device; the handle keeps working on the old one
+    with pytest.raises(sg.SageError):
+        gp.set_devices([0, sg.device_count()])
     ref = [gp.register_frame(_scan(i, (0.2 * i, 0, 0)))[0] for i in range(3)]
     with pytest.raises(sg.SageError, match="fresh"):
         gp.set_devices([1])
@@ -116,6 +119,37 @@ def test_set_devices(orc, cfg):
         other.set_devices([1])
         for i in range(3):
             assert np.array_equal(other.register_frame(_scan(i, (0.2 * i, 0, 0)))[0], ref[i])
+
+
+def test_one_handle_on_two_gpus(orc, cfg):
+    """sage_set_devices(h, {0, 1}, 2): ONE process, the ICP queries of every frame sharded over both GPUs, the sums all-reduced
+    inside the search kernel over peer memory, replicated map updates.  Poses equal the single-GPU ones to rounding (another
+    summation order), the oracle's within the tolerance; the query clouds are identical; reinitialize() clears every replica."""
+    import sage_icp_b200 as sg
+    from sage_icp_b200 import synthetic as syn
+    if sg.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    one, two, op = sg.SagePipeline(cfg), sg.SagePipeline(cfg), orc.OraclePipeline(cfg, threads=orc.max_threads(), evict_faithful=False)
+    two.set_devices([0, 1])
+    assert two.num_devices() == 2
+    n = 25
+    traj = syn.trajectory(n)
+    for rnd in range(2):
+        for i in range(n):
+            scan = syn.make_scan(800 + i, tuple(traj[i]))
+            p1, _, _ = one.register_frame(scan)
+            p2, _, _ = two.register_frame(scan)
+            po, _, _ = op.register_frame(scan)
+            assert float(np.abs(p1 - p2).max()) <= 1e-10, (rnd, i, p1, p2)
+            dt, da = pose_delta(p2, po)
+            assert dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (rnd, i, dt, da)
+            assert two.last_iterations() == one.last_iterations() == op.last_iterations(), (rnd, i)
+            assert np.array_equal(two.last_source(), op.last_source()), (rnd, i)
+        assert two.map().num_voxels() == one.map().num_voxels() == op.map().num_voxels()
+        one.reinitialize(), two.reinitialize(), op.reset()
+        assert two.map().num_voxels() == 0 and len(two.poses()) == 0
+    with pytest.raises(sg.SageError, match="fresh"):
+        two.register_frame(syn.make_scan(1, (0.0, 0.0, 0.0))), two.set_devices([0])
 
 
 def test_bad_config_fails_loudly(cfg):

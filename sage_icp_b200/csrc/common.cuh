@@ -170,11 +170,6 @@ struct IcpState {
     int iter;         // iterations executed
     int done;
     unsigned ticket;  // last-block election
-    unsigned unit_next;  // tile search: units handed out so far in this registration (never reset inside one, see search_tile.cuh)
-    unsigned fetch_base;   // ... value of unit_next at the start of the current iteration
-    unsigned heavy_n[2];   // ... units on the heavy-first queue of the current / the next iteration (by iteration parity)
-    unsigned heavy_ns;     // ... a unit that takes longer than this goes on the next iteration's heavy-first queue
-    unsigned long long unit_ns_sum;  // ... time spent in units during this iteration (sets the next threshold)
     unsigned comm_error;  // fused peer exchange: a peer did not arrive in time
     unsigned long long stat_occupied, stat_candidates;
     unsigned long long stat_scanned, stat_probes, stat_exact, stat_heavy;  // search-kernel work counters (counting launches only)

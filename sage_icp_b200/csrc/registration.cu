@@ -73,9 +73,7 @@ struct IterParams {
     // the capacity of the block's staging area in 16-byte records
     const uint32_t *tile_units, *tile_n_units, *tile_perm;  // tile_perm: sorted position -> index in the caller's array
     double *tile_unit_part;    // [unit][17]
-    uint32_t *tile_heavy_q;    // [2][tile_heavy_cap] heavy-first queues (iteration parity)
-    uint8_t *tile_heavy_flag;  // [2][tile_heavy_cap] 1 = the unit is on that iteration's queue
-    uint32_t tile_heavy_cap;
+    uint32_t *tile_ctl;        // [0] units handed out so far in this registration, [32] its value at the start of the iteration
     uint32_t *tile_group_cnt;  // [group]
     uint32_t tile_stage_cap;
     unsigned long long *dbg;  // optional per-block timeline (tools/perf_probe.py): 4 globaltimer stamps per block + 4 global
@@ -247,11 +245,6 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->iter = 0;
     st->done = (max_iters <= 0);
     st->ticket = 0;
-    st->unit_next = 0;
-    st->fetch_base = 0;
-    st->heavy_n[0] = st->heavy_n[1] = 0;
-    st->heavy_ns = 25000u;  // first guess: twice a typical unit
-    st->unit_ns_sum = 0;
     st->stat_occupied = st->stat_candidates = 0;
     st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = st->stat_staged = 0;
     st->comm_error = 0;
@@ -285,19 +278,38 @@ __device__ __noinline__ uint32_t nn_exact(const IterParams &p, unsigned gmask, i
             if (key_in_range(nx, ny, nz)) found = tbl_find(p.tbl, p.mask, pack_key(nx, ny, nz), blk, cnt) && cnt > 0;
         }
         unsigned fm = __ballot_sync(gmask, found) & gmask;
+        // up to four found voxels per round: their 32-byte loads are independent, so a round costs one trip to memory instead of
+        // four.  Candidates therefore arrive out of enumeration order; the running minimum is kept lexicographically on (metric,
+        // enumeration index: voxel, slot), which is exactly what the reference's strict '<' over the enumeration yields.
         while (fm) {
-            const int l = __ffs(fm) - 1;
-            fm &= fm - 1;
-            const uint32_t b = __shfl_sync(gmask, blk, l), c = __shfl_sync(gmask, cnt, l);
-            const uint32_t ord_base = (uint32_t)(pr0 + (l & (G - 1))) << 16;  // voxel enumeration index : slot
-            const double4 *vp = p.blk_pts + (size_t)b * p.stride;
-            for (uint32_t j = gl; j < c; j += G) {
-                const double4 nb = ldg256(vp + j);
-                const double dx = __dsub_rn(nb.x, cx), dy = __dsub_rn(nb.y, cy), dz = __dsub_rn(nb.z, cz);
-                double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                // semantic metric, core/VoxelHashMap.cpp:87-88
-                if (__double2int_rz(nb.w) == cql || __double2int_rz(__dmul_rn(nb.w, cl)) == 0) d = __dmul_rn(d, th);
-                if (d < best) best = d, best_ord = ord_base + j, best_idx = b * (uint32_t)p.stride + j;
+            uint32_t b[4], c[4], ob[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int l = fm ? __ffs(fm) - 1 : -1;
+                fm &= fm - 1;  // 0 & anything stays 0
+                const int src = l < 0 ? 0 : l;
+                b[u] = __shfl_sync(gmask, blk, src);
+                c[u] = l < 0 ? 0u : __shfl_sync(gmask, cnt, src);
+                ob[u] = (uint32_t)(pr0 + (src & (G - 1))) << 16;  // voxel enumeration index : slot
+            }
+            const uint32_t cmax = max(max(c[0], c[1]), max(c[2], c[3]));
+            for (uint32_t j = gl; j < cmax; j += G) {
+                double4 nb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j < c[u]) nb[u] = ldg256(p.blk_pts + (size_t)b[u] * p.stride + j);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j < c[u]) {
+                        const double dx = __dsub_rn(nb[u].x, cx), dy = __dsub_rn(nb[u].y, cy), dz = __dsub_rn(nb[u].z, cz);
+                        double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        // semantic metric, core/VoxelHashMap.cpp:87-88
+                        if (__double2int_rz(nb[u].w) == cql || __double2int_rz(__dmul_rn(nb[u].w, cl)) == 0) d = __dmul_rn(d, th);
+                        const uint32_t ord = ob[u] + j;
+                        // (best_ord != ~0: DBL_MAX itself never wins in the reference either — its scan starts from DBL_MAX with '<')
+                        if (d < best || (d == best && best_ord != 0xffffffffu && ord < best_ord))
+                            best = d, best_ord = ord, best_idx = b[u] * (uint32_t)p.stride + j;
+                    }
             }
         }
     }
@@ -1030,7 +1042,7 @@ void VoxelMapGPU::init_search_config() {
     const int want = (int)env_long("SAGE_TILE_BLOCKS", per_sm_tile);
     if (want >= 1 && want < per_sm_tile) per_sm_tile = want;
     tile_grid_ = sm_count_ * per_sm_tile;
-    tile_min_ = tile_grid_ > 0 ? (size_t)env_long("SAGE_TILE_MIN", 16384) : 0;
+    tile_min_ = tile_grid_ > 0 ? (size_t)env_long("SAGE_TILE_MIN", 12288) : 0;
     if (tile_grid_ > 0 && tile_min_ < 1) tile_min_ = 1;
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
@@ -1074,7 +1086,7 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
     }
     p.tile_units = tile_units_.p, p.tile_n_units = tile_nunits_.p, p.tile_perm = tile_vals_[1].p, p.tile_stage_cap = tile_stage_cap_;
     p.tile_unit_part = tile_unit_part_.p, p.tile_group_cnt = tile_group_cnt_.p;
-    p.tile_heavy_q = tile_heavy_q_.p, p.tile_heavy_flag = tile_heavy_flag_.p, p.tile_heavy_cap = tile_heavy_cap_;
+    p.tile_ctl = tile_ctl_.p;
 }
 
 // mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points

@@ -90,7 +90,7 @@ __device__ __forceinline__ void scan_bucket_smem(const float4 *s, uint32_t gbase
 
 // shared state of one block of the tile kernel (static shared memory; the staging area is the dynamic part)
 struct TileShared {
-    double acc[kSums][kTileCols];  // the current unit's sums
+    double acc[kSums][kTileCols + 1];  // the current unit's sums, one column per four threads (padded: the publishing lanes read rows)
     Pose est;
     double norm;
     uint32_t gbase[kTileSlots], soff[kTileSlots], cnt[kTileSlots];  // region table: first record (global index), staging offset, records
@@ -147,25 +147,12 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     const uint32_t bar = smem_addr(&sh.mbar);
     const uint32_t n_units = *p.tile_n_units;
     const uint32_t n_groups = (n_units + kTileGroup - 1) / kTileGroup;
-    // Units are handed out by a counter that only grows during a registration; st->fetch_base is its value at the start of this
-    // iteration (the block that finishes the iteration advances it: every block makes exactly one failing fetch per iteration).
-    // Hand-out order: first the units that were slow in the PREVIOUS iteration (the heavy-first queue of this iteration's parity —
-    // a unit far from the map has a dozen open buckets per query and takes three times the mean; started last it would be the
-    // tail of the whole iteration), then the rest in list order.  The order only schedules: every unit's sums go to its own slot.
+    // Units are handed out by a counter that only grows during a registration (p.tile_ctl[0], alone on its cache line: every
+    // block hits it two or three times per iteration); p.tile_ctl[32] is its value at the start of this iteration — every block
+    // makes exactly one failing fetch per iteration, so the block that finishes the iteration advances it by n_units + gridDim.x.
     // (A block that is scheduled so late that the base has already advanced wraps around and leaves without a unit.)
-    const int par = (int)(__ldcg(&st->iter) & 1);
-    const uint32_t fetch_base = __ldcg(&st->fetch_base), n_heavy = __ldcg(&st->heavy_n[par]), heavy_ns = __ldcg(&st->heavy_ns);
-    const uint32_t *heavy_q = p.tile_heavy_q + (size_t)par * p.tile_heavy_cap;
-    const uint8_t *heavy_flag = p.tile_heavy_flag + (size_t)par * p.tile_heavy_cap;
-    auto fetch_unit = [&]() -> uint32_t {  // thread 0 only
-        for (;;) {
-            const uint32_t t = atomicAdd(&st->unit_next, 1u) - fetch_base;
-            if (t < n_heavy) return heavy_q[t];
-            const uint32_t v = t - n_heavy;
-            if (v >= n_units) return 0xffffffffu;
-            if (!heavy_flag[v]) return v;  // else: already handed out from the queue
-        }
-    };
+    const uint32_t fetch_base = __ldcg(p.tile_ctl + 32);
+    auto fetch_unit = [&]() -> uint32_t { return atomicAdd(p.tile_ctl, 1u) - fetch_base; };  // thread 0 only
     // development timeline: thread 0 adds the time since its previous stamp to phase k (the block barriers align the warps)
     unsigned long long t_last = 0;
     if (p.dbg && threadIdx.x == 0) {
@@ -184,16 +171,12 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     unsigned long long n_ranked = 0, n_probes = 0, n_exact = 0, n_pooled = 0, n_staged = 0;  // work counters (COUNT launches only)
 
     uint32_t next_unit = 0;  // thread 0: the unit after the current one, fetched while the current one is being worked on
-    unsigned long long t_unit = 0;
     if (threadIdx.x == 0) sh.unit = fetch_unit();
+    __syncthreads();
     for (;;) {
-        __syncthreads();  // the previous unit is done with the shared state; sh.unit is set
-        const uint32_t u = sh.unit;
+        const uint32_t u = sh.unit;  // set before the last barrier
         if (u >= n_units) break;
-        if (threadIdx.x == 0) {
-            t_unit = gtime();
-            next_unit = fetch_unit();  // its latency hides behind phase A
-        }
+        if (threadIdx.x == 0) next_unit = fetch_unit();  // its latency hides behind phase A
         TILE_STAMP(8);
         const uint32_t ubeg = p.tile_units[u], uend = p.tile_units[u + 1];  // at most kTileThreads queries by construction
         const uint32_t q = ubeg + threadIdx.x;
@@ -488,29 +471,24 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
         }
         TILE_STAMP(7);
         // ---- I: publish the unit's sums; the block that completes a group adds it; the one that completes the last group steps ------
-        __syncthreads();
-        for (int k = warp; k < kSums; k += kTileWarps) {
-            double v = sh.acc[k][lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-            if (lane == 0) p.tile_unit_part[(size_t)u * kSums + k] = v;
-        }
-        if (threadIdx.x == 0) {  // how long the unit took decides whether it goes first next time
-            const unsigned long long ns = gtime() - t_unit;
-            atomicAdd(&st->unit_ns_sum, ns);
-            uint8_t heavy = 0;
-            if (ns > heavy_ns) {
-                const uint32_t slot = atomicAdd(&st->heavy_n[par ^ 1], 1u);
-                if (slot < p.tile_heavy_cap) p.tile_heavy_q[(size_t)(par ^ 1) * p.tile_heavy_cap + slot] = u, heavy = 1;
-            }
-            p.tile_heavy_flag[(size_t)(par ^ 1) * p.tile_heavy_cap + u] = heavy;
-        }
-        __threadfence();
-        __syncthreads();
         const uint32_t g = u / kTileGroup;
         const uint32_t gfirst = g * kTileGroup, gsize = min((uint32_t)kTileGroup, n_units - gfirst);
-        if (threadIdx.x == 0) sh.flag = (atomicAdd(&p.tile_group_cnt[g], 1u) == gsize - 1) ? 1 : 0;
-        __syncthreads();
+        __syncthreads();  // every warp has written its columns
+        if (warp == 0) {  // one warp publishes (lane k adds the 32 columns of sum k in order); the others go and wait at the barrier
+            if (lane < kSums) {
+                double v = 0;
+#pragma unroll 8
+                for (int c = 0; c < kTileCols; ++c) v += sh.acc[lane][c];
+                p.tile_unit_part[(size_t)u * kSums + lane] = v;
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) {
+                sh.flag = (atomicAdd(&p.tile_group_cnt[g], 1u) == gsize - 1) ? 1 : 0;
+                sh.unit = next_unit;
+            }
+        }
+        __syncthreads();  // flag and the next unit are set; everybody is done with this unit's shared state
         if (sh.flag) {
             __threadfence();
             if (threadIdx.x < kSums) {
@@ -526,21 +504,12 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
             }
             __syncthreads();
             if (sh.flag == 2) {
-                if (threadIdx.x == 0) {  // every unit of this iteration is done: set up the next one's hand-out
-                    __threadfence();
-                    const uint32_t queued = min(__ldcg(&st->heavy_n[par ^ 1]), p.tile_heavy_cap);
-                    st->heavy_n[par ^ 1] = queued;
-                    st->heavy_n[par] = 0;  // rebuilt during the next iteration, for the one after
-                    st->fetch_base = fetch_base + n_units + n_heavy + gridDim.x;
-                    const unsigned long long mean = __ldcg(&st->unit_ns_sum) / n_units;
-                    st->heavy_ns = (unsigned)min(mean + mean / 2ull, 4000000000ull);  // heavy = half as long again as the mean unit
-                    st->unit_ns_sum = 0;
-                }
+                if (threadIdx.x == 0) p.tile_ctl[32] = fetch_base + n_units + gridDim.x;  // every unit of this iteration is done
                 reduce_and_step(p, n_groups, sh.est, sh.norm, tag);
             }
+            __syncthreads();  // sh.flag is rewritten by the next unit's publish
         }
         if (p.dbg && threadIdx.x == 0) sh.dbg_t[10] += 1, sh.dbg_t[11] += uend - ubeg;
-        if (threadIdx.x == 0) sh.unit = next_unit;
     }
     if (p.dbg && threadIdx.x == 0) {
         sh.dbg_t[9] = gtime();

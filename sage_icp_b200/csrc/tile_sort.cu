@@ -190,11 +190,8 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
     tile_group_cnt_.ensure(groups);
     SAGE_CUDA(cudaMemsetAsync(tile_group_cnt_.p, 0, groups * sizeof(uint32_t), stream_));
     if ((size_t)17 * groups > partials_.cap) partials_.ensure((size_t)17 * groups);
-    // heavy-first queues: units that were slow in one iteration are handed out first in the next (search_tile.cuh)
-    tile_heavy_q_.ensure(2 * (n + 1));
-    tile_heavy_flag_.ensure(2 * (n + 1));
-    tile_heavy_cap_ = (uint32_t)(n + 1);
-    SAGE_CUDA(cudaMemsetAsync(tile_heavy_flag_.p, 0, 2 * (n + 1), stream_));
+    tile_ctl_.ensure(64);
+    SAGE_CUDA(cudaMemsetAsync(tile_ctl_.p, 0, 64 * sizeof(uint32_t), stream_));  // hand-out counter and base restart at 0
     const size_t tmp_bytes = sort_pairs_tmp_bytes_u32(n, kKeyBitsTile);
     tile_tmp_.ensure(tmp_bytes ? tmp_bytes : 1);
     SAGE_LAUNCH(tile_key_kernel, (n32 + 255) / 256, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, voxel_size_, tile_keys_[0].p,

@@ -192,9 +192,7 @@ private:
     DevBuf<uint8_t> tile_tmp_, tile_flag_;  // sort scratch; unit-head flag per sorted position
     DevBuf<double> tile_unit_part_;      // [unit][17] sums of one unit
     DevBuf<uint32_t> tile_group_cnt_;    // units of a group that have published their sums
-    DevBuf<uint32_t> tile_heavy_q_;      // [2][cap] units to hand out first in the even / odd iterations (they were slow in the previous one)
-    DevBuf<uint8_t> tile_heavy_flag_;    // [2][cap]
-    uint32_t tile_heavy_cap_ = 0;
+    DevBuf<uint32_t> tile_ctl_;          // unit hand-out counter and its per-iteration base, each on its own cache line
     int tile_grid_ = 0;            // co-resident blocks of the tile kernels
     int tile_minb_ = 6;            // which instantiation: 6 (80 registers) or 4 (128 registers) resident blocks per SM aimed at
     size_t tile_min_ = 0;          // scans of at least this many queries take the tile search (0 = never)

@@ -35,7 +35,7 @@ def pytest_collection_modifyitems(config, items):
 # How the correspondence search is scheduled is an implementation choice the results must not depend on: the parity tests that
 # use this fixture run once per schedule.  The library reads these variables when a map first searches (registration.cu).
 SEARCH_MODES = {
-    "default": {},                                                              # tile search from 16 384 queries up
+    "default": {},                                                              # tile search from 12 288 queries up
     # tile search forced for every size and density (SAGE_TILE_FILL=0 switches off the "units must be well filled" rule)
     "tile": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0"},                                      # persistent loop, 96 registers
     "tile_launch": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0", "SAGE_TILE_PERSISTENT": "0", "SAGE_TILE_MINB": "8", "SAGE_TILE_STAGE": "704"},

@@ -49,7 +49,7 @@ def _check_corr(g, o, q, max_dist, th):
 @pytest.mark.parametrize("env", [{}, {"SAGE_TILE_STAGE": "128"}, {"SAGE_TILE_MINB": "4"}, {"SAGE_TILE_MINB": "8", "SAGE_TILE_BLOCKS": "2"}],
                          ids=["default", "tiny_staging", "128_registers", "64_registers_2_blocks_per_sm"])
 def test_tile_correspondences_bit_exact_on_a_full_scan(orc, monkeypatch, env):
-    """32 000 queries of a street scan (above the 16 384-query threshold): every query's target equals the oracle's, in the
+    """32 000 queries of a street scan (above the 12 288-query threshold): every query's target equals the oracle's, in the
     caller's order, whether the buckets fit the staging area or are scanned from global memory, for each register budget."""
     pts = _street()
     g = _maps(orc, pts, monkeypatch, env)
@@ -58,7 +58,7 @@ def test_tile_correspondences_bit_exact_on_a_full_scan(orc, monkeypatch, env):
     scan, _ = _queries()
     q = scan.copy()
     q[:, 2] += 1.73
-    assert len(q) >= 16384
+    assert len(q) >= 12288
     assert _check_corr(g, o, q, 3.0, 0.4) > 20000
     scanned, probes, exact, heavy, staged = g.search_work(q, 3.0, 0.4, with_staged=True)
     assert staged > 0  # the buckets really went through the bulk copies

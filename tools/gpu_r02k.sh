@@ -1,0 +1,14 @@
+#!/bin/bash
+# round 2, visit K: whole GPU suite on the settled kernel, bench (all objects), launch list + full ncu capture of the tile kernel
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/r02k_gpu.txt 2>&1
+nproc > gpurun_out/r02k_nproc.txt; lscpu | grep 'Model name' >> gpurun_out/r02k_nproc.txt
+timeout 1500 python -m pytest tests -m gpu -q --timeout=600 > gpurun_out/r02k_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r02k_pytest.log
+tail -8 gpurun_out/r02k_pytest.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/r02k_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r02k_smoke.log; tail -2 gpurun_out/r02k_smoke.log
+timeout 900 python bench.py > gpurun_out/r02k_bench.json 2> gpurun_out/r02k_bench.err; echo "bench rc=$?"; cat gpurun_out/r02k_bench.json; tail -3 gpurun_out/r02k_bench.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r02k_bench_reference.json 2> gpurun_out/r02k_bench_reference.err; cut -c1-300 gpurun_out/r02k_bench_reference.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 400 --csv --log-file gpurun_out/r02k_launches.csv \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-pipeline --no-hbm-regime > gpurun_out/r02k_bench_under_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:nn_tile -s 4 -c 1 -f -o gpurun_out/r02k_tile \
+    python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-pipeline --no-hbm-regime > gpurun_out/r02k_bench_under_ncu_full.log 2>&1; echo "ncu rc=$?"

@@ -17,10 +17,11 @@ CONFIGS = {
     "tile_minb4_stage2560": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "4", "SAGE_TILE_STAGE": "2560"},
     "tile_minb5_stage1024": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "5", "SAGE_TILE_STAGE": "1024"},
     "tile_stage2048": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "2048"},
+    "tile_no_heavy_first": {"SAGE_TILE_MIN": "1", "SAGE_TILE_HEAVY": "0"},
     "tile_blocks4": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "4"},
     "tile_blocks3": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "3"},
 }
-KEYS = ("SAGE_TILE", "SAGE_TILE_FILL", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS")
+KEYS = ("SAGE_TILE", "SAGE_TILE_HEAVY", "SAGE_TILE_FILL", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS")
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CONFIGS)
 sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2000, 8000, 15000, 30000, 60000, 120000]
 n_map = int(sys.argv[3]) if len(sys.argv) > 3 else 5_000_000
@@ -83,6 +84,10 @@ if os.environ.get("TILE_TIMELINE", "1") != "0":
     print(f"tile timeline: {len(b)} blocks, start spread {b[:,0].max()-t0} ns, block end (before finish) med {np.median(b[:,9]-t0):.0f} p90 "
           f"{np.percentile(b[:,9]-t0,90):.0f} max {(b[:,9]-t0).max()} ns; units/block med {np.median(b[:,10]):.1f} max {b[:,10].max()}, "
           f"queries/block med {np.median(b[:,11]):.0f} max {b[:,11].max()}")
+    order_ = np.argsort(-(b[:, 9] - t0))[:8]
+    print("   slowest blocks: end | units queries | fetch A C wait D E FG H (ns, summed over the block's units)")
+    for i_ in order_:
+        print(f"      {b[i_,9]-t0:7d} | {b[i_,10]:2d} {b[i_,11]:4d} | " + " ".join(f"{b[i_,k_]:6d}" for k_ in (8, 1, 2, 3, 4, 5, 6, 7)))
     tail = buf[K * g:K * g + 8].astype(np.int64)
     print(f"   last block: enters reduce {tail[0]-t0} ns, sums reduced/exchanged +{tail[1]-tail[0]}, 6x6 solved +{tail[5]-tail[1]}, exp +{tail[6]-tail[5]}, "
           f"step done +{tail[2]-tail[6]} (total {tail[2]-tail[0]} ns)")

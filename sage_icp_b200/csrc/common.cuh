@@ -171,6 +171,7 @@ struct IcpState {
     int done;
     unsigned ticket;  // last-block election
     unsigned comm_error;  // fused peer exchange: a peer did not arrive in time
+    unsigned declined;    // tile search: the units are too thinly filled, nothing was done — the host runs the per-query kernel instead
     unsigned long long stat_occupied, stat_candidates;
     unsigned long long stat_scanned, stat_probes, stat_exact, stat_heavy;  // search-kernel work counters (counting launches only)
     unsigned long long stat_staged;  // tile search: records pulled into shared memory by bulk copies

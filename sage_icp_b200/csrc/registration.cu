@@ -73,6 +73,7 @@ struct IterParams {
     // the capacity of the block's staging area in 16-byte records
     const uint32_t *tile_units, *tile_n_units, *tile_perm;  // tile_perm: sorted position -> index in the caller's array
     double *tile_unit_part;    // [unit][17]
+    uint32_t tile_fill;        // mean queries per unit below which the kernel declines (0: never)
     uint32_t *tile_ctl;        // [0] units handed out so far in this registration, [32] its value at the start of the iteration
     uint32_t *tile_group_cnt;  // [group]
     uint32_t tile_stage_cap;
@@ -248,6 +249,7 @@ __global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double 
     st->stat_occupied = st->stat_candidates = 0;
     st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = st->stat_staged = 0;
     st->comm_error = 0;
+    st->declined = 0;
 }
 
 __global__ void icp_solve_kernel(IcpState *st) {  // <<<1, 64>>>, after the NCCL all-reduce of the sums
@@ -1086,7 +1088,7 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
     }
     p.tile_units = tile_units_.p, p.tile_n_units = tile_nunits_.p, p.tile_perm = tile_vals_[1].p, p.tile_stage_cap = tile_stage_cap_;
     p.tile_unit_part = tile_unit_part_.p, p.tile_group_cnt = tile_group_cnt_.p;
-    p.tile_ctl = tile_ctl_.p;
+    p.tile_ctl = tile_ctl_.p, p.tile_fill = 0;
 }
 
 // mode 0: ICP iteration (apply est, solve on device when single rank); mode 1: correspondences/sums of the points
@@ -1162,6 +1164,7 @@ void VoxelMapGPU::launch_tile(size_t n, double max_dist, double kernel, double s
     IterParams p;
     fill_params(p, src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr);
     p.dbg = dbg_on_ ? dbg_.p : nullptr;
+    p.tile_fill = comm_ == nullptr ? (uint32_t)tile_fill_ : 0u;  // NCCL variant: decided on the host (register_frame_dev)
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
     prof_begin();
     if (persistent_iters > 0) {
@@ -1203,14 +1206,15 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     if (tile) {
         tile_prepare(frame, n, guess, true);
         sorted = true;  // src_ = the queries in cell order, initial guess applied
-        // The tile search pays per unit, so it needs units that are well filled (a scan: tens of queries per cell).  Queries spread
-        // thinly over the map (one per cell: BASELINE configs[4]'s uniform set, a voxel-downsampled cloud) are served better by the
-        // per-query kernel — which takes the sorted array as it is.  The unit count is known once the sort has run.
-        tile_nunits_pin_.ensure(1);
-        SAGE_CUDA(cudaMemcpyAsync(tile_nunits_pin_.p, tile_nunits_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-        SAGE_CUDA(cudaStreamSynchronize(stream_));
-        last_units_ = *tile_nunits_pin_.p;
-        if ((size_t)last_units_ * tile_fill_ > n) tile = false;
+        // A query set spread thinly over the map is declined by the kernel itself (`declined` below, search_tile.cuh).  Only the NCCL
+        // variant decides here, with a read-back of the unit count: its all-reduce launches must match on every rank.
+        if (comm_ != nullptr) {
+            tile_nunits_pin_.ensure(1);
+            SAGE_CUDA(cudaMemcpyAsync(tile_nunits_pin_.p, tile_nunits_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+            SAGE_CUDA(cudaStreamSynchronize(stream_));
+            last_units_ = *tile_nunits_pin_.p;
+            if ((size_t)last_units_ * tile_fill_ > n) tile = false;
+        }
     } else if (n) {
         SAGE_CUDA(cudaMemcpyAsync(src_.p, frame, n * sizeof(double4), cudaMemcpyDeviceToDevice, stream_));
     }
@@ -1219,6 +1223,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     // batches; the first batch is sized from the previous registration so that the common case needs one round trip
     int launched = 0;
     bool persistent = false;
+    const size_t prof_mark = prof_used_;
     if (tile && tile_persistent_ && comm_ == nullptr && !dbg_on_) {
         launch_tile(n, max_dist, kernel, sem_th, 0, max_iters);
         persistent = true;
@@ -1247,6 +1252,25 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
         SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
         SAGE_CUDA(cudaStreamSynchronize(stream_));
         if (icp_pin_.p->done) break;
+    }
+    if (tile && icp_pin_.p->declined) {
+        // The tile kernel found its units too thinly filled (BASELINE configs[4]'s uniform queries, a voxel-downsampled cloud) and
+        // did nothing: the per-query kernel takes the sorted array as it is.  No exchange has happened yet, so the ranks stay in step
+        // whatever each of them decides.
+        tile = false;
+        prof_used_ = prof_mark;  // the declined launches did no work: they are not iterations
+        SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, guess, max_iters, est_th);
+        launched = 0;
+        while (launched < max_iters) {
+            int batch = launched == 0 ? (last_iters_ + 2 > 8 ? last_iters_ + 2 : 8) : 8;
+            if (batch > 48) batch = 48;
+            if (batch > max_iters - launched) batch = max_iters - launched;
+            for (int b = 0; b < batch; ++b) launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, 0, launched + b, true);
+            launched += batch;
+            SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
+            SAGE_CUDA(cudaStreamSynchronize(stream_));
+            if (icp_pin_.p->done) break;
+        }
     }
     // exchanges completed: every rank ran the same iterations (lock-step), whichever launch mode each of them chose
     if (peer_world_ > 1) xchg_tag_ += (unsigned long long)icp_pin_.p->iter;

@@ -71,18 +71,24 @@ def make_queries(step: int, n_beams: int, n_az: int, half_len: float):
     return scan, guess
 
 
+SECTORS_PER_RANK = 4
+
+
 def shard_of(scan: np.ndarray, rank: int, world: int, n_az: int = 0) -> np.ndarray:
     """Rank `rank`'s share of a scan.  Any partition gives the same sums.  A spinning lidar delivers its points azimuth by azimuth,
     so a contiguous index range of a real scan is an angular sector; the synthetic scans are stored beam by beam (n_beams x n_az),
-    so the same sector is the column range [rank, rank + 1) * n_az / world of every beam.  A sector is spatially compact — each
-    rank works on its own cells of the map (what the tile search wants) — and holds every beam, near and far, so the ranks are
-    balanced.  Without the scan shape: chunks of 32 consecutive points dealt round-robin."""
+    so the same sector is a column range of every beam.  A sector is spatially compact — each rank works on its own cells of the
+    map, which is what the tile search wants — and holds every beam, near and far.  Every rank gets SECTORS_PER_RANK thin sectors
+    spread around the circle (sector s belongs to rank s % world), so that one rank does not get the whole dense side of the
+    street: the ranks advance in lock-step, an iteration takes as long as the slowest of them.  Without the scan shape: chunks of
+    32 consecutive points dealt round-robin."""
     if world == 1:
         return np.ascontiguousarray(scan)
     if n_az and len(scan) % n_az == 0:
         rows = scan.reshape(len(scan) // n_az, n_az, scan.shape[1])
-        lo, hi = n_az * rank // world, n_az * (rank + 1) // world
-        return np.ascontiguousarray(rows[:, lo:hi].reshape(-1, scan.shape[1]))
+        n_sec = world * SECTORS_PER_RANK
+        cols = np.concatenate([np.arange(n_az * s // n_sec, n_az * (s + 1) // n_sec) for s in range(rank, n_sec, world)])
+        return np.ascontiguousarray(rows[:, cols].reshape(-1, scan.shape[1]))
     n_chunks = (len(scan) + 31) // 32
     owner = np.repeat(np.arange(n_chunks) % world, 32)[: len(scan)]
     return np.ascontiguousarray(scan[owner == rank])
@@ -257,7 +263,7 @@ def workload_config(args, map_points, map_voxels):
             "scan_rays": args.beams * args.az, "map_points": int(map_points), "map_voxels": int(map_voxels), "gn_iterations": ITERS,
             "max_correspondence_distance": MAX_DIST, "kernel": KERNEL, "sem_th": SEM_TH,
             "l2": "L2 flushed (256 MiB write) between timed steps; each step timed with its own CUDA-event pair",
-            "parallelism": (f"query-shard x{args.gpus} (azimuth sectors) + replicated map, all-reduce of the 17 normal-equation sums "
+            "parallelism": (f"query-shard x{args.gpus} (4 azimuth sectors per rank) + replicated map, all-reduce of the 17 normal-equation sums "
                             + ("fused into the search kernel over NVLink peer memory" if args.comm == "peer" else "by NCCL")) if args.gpus > 1 else "single GPU"}
 
 

@@ -1048,12 +1048,18 @@ void VoxelMapGPU::init_search_config() {
     if (tile_grid_ > 0 && tile_min_ < 1) tile_min_ = 1;
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
-    tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 48);  // mean queries per unit below which the per-query kernel takes the scan
+    tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 1);  // 0: the tile search never declines a thinly spread query set
     {
         const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
         xchg_timeout_ns_ = (unsigned long long)(t < 1 ? 1 : t) * 1000000000ull;
     }
     partials_.ensure((size_t)kSums * (nn_grid_ > tile_grid_ ? nn_grid_ : tile_grid_));
+}
+
+// the rule by which nn_tile_iteration declines a query set (search_tile.cuh), for the paths that decide on the host
+bool VoxelMapGPU::tile_units_too_thin(uint32_t n_units, size_t n) const {
+    const unsigned long long rounds = ((unsigned long long)n_units + tile_grid_ - 1) / (unsigned long long)tile_grid_;
+    return rounds * 15000ull + 12000ull > 30000ull + (unsigned long long)n * 48ull / 100ull;
 }
 
 void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_dist, double kernel, double sem_th, int mode, double4 *tgt_out,
@@ -1106,7 +1112,7 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         SAGE_CUDA(cudaStreamSynchronize(stream_));
         last_units_ = *tile_nunits_pin_.p;
     }
-    if (mode != 0 && tile_min_ > 0 && n >= tile_min_ && (size_t)last_units_ * tile_fill_ <= n) {  // same rule as register_frame_dev
+    if (mode != 0 && tile_min_ > 0 && n >= tile_min_ && !(tile_fill_ && tile_units_too_thin(last_units_, n))) {  // same rule as the kernel's
         IterParams p;
         fill_params(p, src_.p, n, max_dist, kernel, sem_th, mode, tgt_out, matched_out);
         const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
@@ -1213,7 +1219,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
             SAGE_CUDA(cudaMemcpyAsync(tile_nunits_pin_.p, tile_nunits_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
             SAGE_CUDA(cudaStreamSynchronize(stream_));
             last_units_ = *tile_nunits_pin_.p;
-            if ((size_t)last_units_ * tile_fill_ > n) tile = false;
+            if (tile_fill_ && tile_units_too_thin(last_units_, n)) tile = false;
         }
     } else if (n) {
         SAGE_CUDA(cudaMemcpyAsync(src_.p, frame, n * sizeof(double4), cudaMemcpyDeviceToDevice, stream_));

@@ -146,13 +146,19 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     const float vs32 = p.vs32, th32 = p.th32;
     const uint32_t bar = smem_addr(&sh.mbar);
     const uint32_t n_units = *p.tile_n_units;
-    // The tile search pays per unit, so it needs well-filled units.  A query set that is spread thinly over the map (fewer than
-    // tile_fill queries per unit) is declined here, grid-uniformly and before anything is touched: the host sees the flag at its
-    // next read-back and runs the per-query kernel on the (already sorted) array.  Deciding on the device keeps a host round trip
-    // out of every ordinary registration.
-    if ((unsigned long long)n_units * p.tile_fill > p.n || __ldcg(&st->declined)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) st->declined = 1, st->done = 1;
-        return;
+    // The tile search pays per unit (~15 us of dependent latency for each round of gridDim.x units, ~12 us per iteration for the
+    // reduction and the step); the per-query kernel pays ~30 us + 0.48 ns per query (both measured on B200, profiles/
+    // r02_tile_kernel.md).  A query set that is spread so thinly over the map that its units would take longer than that — BASELINE
+    // configs[4]'s uniform queries: one unit per query — is declined here, grid-uniformly and before anything is touched: the host
+    // sees the flag at its next read-back and runs the per-query kernel on the (already sorted) array.  Deciding on the device keeps a
+    // host round trip out of every ordinary registration.  tile_fill == 0: never decline (tests force a schedule).
+    {
+        const unsigned long long rounds = (n_units + gridDim.x - 1) / gridDim.x;
+        const bool thin = p.tile_fill != 0 && rounds * 15000ull + 12000ull > 30000ull + (unsigned long long)p.n * 48ull / 100ull;
+        if (thin || __ldcg(&st->declined)) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) st->declined = 1, st->done = 1;
+            return;
+        }
     }
     const uint32_t n_groups = (n_units + kTileGroup - 1) / kTileGroup;
     // Units are handed out by a counter that only grows during a registration (p.tile_ctl[0], alone on its cache line: every

@@ -198,7 +198,8 @@ private:
     size_t tile_min_ = 0;          // scans of at least this many queries take the tile search (0 = never)
     uint32_t tile_stage_cap_ = 0;  // staging area of a block, in 16-byte records
     bool tile_persistent_ = true;  // whole GN loop in one cooperative launch
-    size_t tile_fill_ = 48;        // mean queries per unit the tile search needs to beat the per-query kernel
+    size_t tile_fill_ = 1;         // 1: thinly spread query sets go to the per-query kernel (tile_units_too_thin); 0: never
+    bool tile_units_too_thin(uint32_t n_units, size_t n) const;
     uint32_t last_units_ = 0;      // units of the last sorted scan
     PinBuf<uint32_t> tile_nunits_pin_;
     bool coop_ok_ = false;

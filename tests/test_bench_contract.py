@@ -50,6 +50,12 @@ def test_shard_of_partitions_a_scan():
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 32
     odd = scan[:1001]
     assert sum(len(bench.shard_of(odd, r, 3)) for r in range(3)) == 1001
+    # with the scan shape: azimuth sectors (several thin ones per rank), still a partition, balanced to a few columns of 64 beams
+    for world in (2, 4, 8):
+        parts = [bench.shard_of(scan, r, world, n_az=1875) for r in range(world)]
+        allp = np.concatenate(parts)
+        assert len(allp) == len(scan) and np.array_equal(np.sort(allp[:, 0]), scan[:, 0])
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 64 * bench.SECTORS_PER_RANK
 
 
 def test_reference_arm_uses_every_host_core_under_torchrun():

@@ -580,30 +580,38 @@ __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t co
         const int t = threadIdx.x;
         const size_t slot = ((size_t)(tag & 1ull) * kMaxPeers) * kXchgSlot;
         if (t < p.xchg_world) {
+            // payload, then the tag with a RELEASE store at system scope: it orders this thread's own payload stores before the
+            // tag as seen by the peer, which is all that is needed — no device-wide fence.sc.sys (MEMBAR.SC.SYS drains every
+            // outstanding store of the SM and cost several microseconds per iteration in round 1)
             double *dst = p.xchg_peer[t] + slot + (size_t)p.xchg_rank * kXchgSlot;
 #pragma unroll
-            for (int k = 0; k < kSums; ++k) dst[k] = s_sums[k];
-            __threadfence_system();
-            *reinterpret_cast<volatile unsigned long long *>(dst + kSums) = tag;
+            for (int k = 0; k < kSums; ++k) asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(dst + k), "d"(s_sums[k]) : "memory");
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + kSums), "l"(tag) : "memory");
         }
-        __syncthreads();
         if (t < p.xchg_world) {
-            const volatile unsigned long long *flag =
-                reinterpret_cast<const volatile unsigned long long *>(p.xchg_peer[p.xchg_rank] + slot + (size_t)t * kXchgSlot + kSums);
+            // wait for rank t's tag in this rank's own buffer (ACQUIRE at system scope), then its payload is visible
+            const unsigned long long *flag =
+                reinterpret_cast<const unsigned long long *>(p.xchg_peer[p.xchg_rank] + slot + (size_t)t * kXchgSlot + kSums);
             const unsigned long long t0 = gtime();
-            while (*flag != tag) {
+            unsigned long long seen = 0;
+            while (true) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+                if (seen == tag) break;
                 if (gtime() - t0 > p.xchg_timeout_ns) {
                     st->comm_error = 1;
                     break;
                 }
             }
-            __threadfence_system();
         }
         __syncthreads();
         if (t < kSums) {
-            const volatile double *mine = p.xchg_peer[p.xchg_rank] + slot;
+            const double *mine = p.xchg_peer[p.xchg_rank] + slot;
             double v = 0;
-            for (int r = 0; r < p.xchg_world; ++r) v += mine[(size_t)r * kXchgSlot + t];
+            for (int r = 0; r < p.xchg_world; ++r) {
+                double a;
+                asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(a) : "l"(mine + (size_t)r * kXchgSlot + t) : "memory");
+                v += a;
+            }
             st->sums[t] = v, s_sums[t] = v;
         }
         __syncthreads();

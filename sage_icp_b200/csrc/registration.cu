@@ -144,8 +144,11 @@ __device__ __noinline__ void icp_solve_xi(const double *S, double xi[6]) {
     // rounding noise there, not 0, and dividing by it would throw the pose far away.  The reference's LDLT divides by whatever
     // pivot rounding leaves (Eigen zeroes only pivots below 1/highest()), so its step is noise-dominated too; here the step
     // degrades to the translation that aligns the weighted centroids (o = 0, u = b_t / w), which is bounded by the residuals.
+    // Two ways of being singular up to rounding: the centred second moments M are entirely cancellation noise of the uncentred
+    // ones (all sources coincide: tr M <= 1e-13 * sum w |s|^2), or M itself has a null direction (sources on a line: |det M| <=
+    // 1e-12 (tr M / 3)^3).  A well-conditioned system is twelve orders of magnitude away from either.
     const double tr = (m00 + m11 + m22) * (1.0 / 3.0);
-    if (!(fabs(det) > 1e-12 * tr * tr * tr)) {
+    if (!(tr > 1e-13 * ((xx + yy) + zz)) || !(fabs(det) > 1e-12 * tr * tr * tr)) {
         xi[0] = btx * iw, xi[1] = bty * iw, xi[2] = btz * iw;
         return;
     }

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "nccl_shim.cuh"
+#include <cstdlib>
 #include "voxel_map.cuh"
 
 namespace sage {
@@ -413,7 +414,9 @@ void VoxelMapGPU::reserve(size_t extra) {
     const bool need_blocks = hi_bound_ + extra > blk_cap_;
     const bool need_tbl = 2 * (live_bound_ + extra) > tbl_cap_;
     if (need_blocks || need_tbl) sync_stats();  // tighten the bounds before paying for growth
+    static const bool trace = getenv("SAGE_TRACE_GROWTH") != nullptr;
     if (hi_bound_ + extra > blk_cap_) {
+        if (trace) fprintf(stderr, "[sage] block pool grows: hi_bound %zu + %zu > cap %u (n_hi %u, live %u)\n", hi_bound_, extra, blk_cap_, host_stats_.n_hi, host_stats_.n_live);
         size_t want = std::max<size_t>(hi_bound_ + extra, (size_t)blk_cap_ * 2);
         // first allocation: room for 64 Ki voxels (126 MB with 40 slots per voxel) so that a streaming map does not pay a
         // reallocate-and-copy step (cudaMalloc + cudaFree: ~10 ms, device-synchronising) every time it doubles early in a drive
@@ -436,6 +439,7 @@ void VoxelMapGPU::reserve(size_t extra) {
                                                 blk_pts_.cap / (size_t)stride_, blk_hot_.cap / (size_t)stride_});
     }
     if (2 * (live_bound_ + extra) > tbl_cap_) {
+        if (trace) fprintf(stderr, "[sage] table grows: 2 * (live_bound %zu + %zu) > cap %u\n", live_bound_, extra, tbl_cap_);
         uint32_t cap = tbl_cap_;
         while ((size_t)cap < 2 * (live_bound_ + extra)) cap *= 2;
         rebuild_table(cap);

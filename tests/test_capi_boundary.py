@@ -284,3 +284,19 @@ def test_bad_config_is_refused_before_any_device_work(lib, cfg):
     keep = pod.voxel_size
     pod.voxel_size = None
     assert L.sage_create(C.byref(pod), 0) is None and b"voxel_size" in L.sage_last_error()
+
+
+def test_python_harness_refuses_inconsistent_inputs():
+    """The ctypes harness must not hand the library lengths it has not checked: a group count taken from voxel_size with offsets taken
+    from voxel_labels, or a flat array passed as a cloud, would make the library read past the end of a buffer."""
+    from sage_icp_b200.capi import _pts
+    from sage_icp_b200.config import launch_config
+    cfg = launch_config()
+    cfg.voxel_size = cfg.voxel_size + [0.5]  # one more size than label groups
+    with pytest.raises(ValueError, match="voxel_labels has 6 groups but voxel_size has 7"):
+        cfg.to_pod()
+    with pytest.raises(ValueError, match=r"\(n, 4\)"):
+        _pts(np.zeros(12))
+    with pytest.raises(ValueError, match=r"\(n, 4\)"):
+        _pts(np.zeros((5, 3)))
+    assert _pts(np.zeros((0,))).shape == (0, 4) and _pts([[1, 2, 3, 4]]).shape == (1, 4)

@@ -292,3 +292,28 @@ def test_degenerate_batch_into_one_voxel(orc):
     assert time.time() - t < 20.0
     o.add_points(pts)
     assert_maps_equal(g.dump(), o.dump())
+
+
+@pytest.mark.parametrize("case", ["one_pair", "two_pairs", "collinear"])
+def test_rank_deficient_systems_take_a_bounded_step(orc, case):
+    """One or two correspondences, or collinear ones (track loss, a scan leaving the map): the 3x3 rotation block of the normal
+    equations is singular up to rounding.  Dividing by that noise would throw the pose far away; the step must degrade to the
+    translation that aligns the weighted centroids instead (registration.cu icp_solve_xi).  The query ends on its target, the
+    rotation stays the identity, nothing explodes."""
+    import sage_icp_b200 as sg
+    g = sg.SageMap(0.8, 1e9, 20, 20, BASIC_LABELS)
+    if case == "one_pair":
+        pts = np.array([[10.3, 4.1, 0.7, 40.0]])
+    elif case == "two_pairs":
+        pts = np.array([[10.3, 4.1, 0.7, 40.0], [30.9, -7.2, 1.1, 50.0]])
+    else:
+        t = np.linspace(0.0, 40.0, 30)
+        pts = np.c_[5.0 + t, 2.0 + 0.5 * t, 0.3 + 0.1 * t, np.full(30, 40.0)]
+    g.add_points(pts)
+    q = pts.copy()
+    q[:, :3] += np.array([0.21, -0.13, 0.08])  # a pure translation well inside max_dist
+    guess = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    pose, it = g.register_frame(q, guess, 3.0, 1.0 / 3.0, 0.4, max_iters=50)
+    assert np.all(np.isfinite(pose)) and it <= 50
+    assert np.linalg.norm(pose[:3] - np.array([-0.21, 0.13, -0.08])) < 1e-6, pose
+    assert np.linalg.norm(pose[3:6]) < 1e-9 and abs(pose[6] - 1.0) < 1e-12, pose

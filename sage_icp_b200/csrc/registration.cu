@@ -72,6 +72,7 @@ struct IterParams {
     // tile search (search_tile.cuh): unit boundaries in the sorted query array [n_units + 1], their number (device scalar), and
     // the capacity of the block's staging area in 16-byte records
     const uint32_t *tile_units, *tile_n_units, *tile_perm;  // tile_perm: sorted position -> index in the caller's array
+    const uint32_t *tile_order;  // hand-out order of the units (largest first); null = list order
     double *tile_unit_part;    // [unit][17]
     uint32_t tile_fill;        // mean queries per unit below which the kernel declines (0: never)
     uint32_t *tile_ctl;        // [0] units handed out so far in this registration, [32] its value at the start of the iteration
@@ -1059,6 +1060,7 @@ void VoxelMapGPU::init_search_config() {
     if (tile_grid_ > 0 && tile_min_ < 1) tile_min_ = 1;
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
+    tile_by_size_ = env_long("SAGE_TILE_BY_SIZE", 1) != 0;
     tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 1);  // 0: the tile search never declines a thinly spread query set
     {
         const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
@@ -1103,7 +1105,7 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
         p.xchg_world = peer_world_, p.xchg_rank = peer_rank_, p.xchg_tag = xchg_tag_ + 1;  // + iteration index (callers)
         for (int k = 0; k < peer_world_; ++k) p.xchg_peer[k] = peer_buf_[k];
     }
-    p.tile_units = tile_units_.p, p.tile_n_units = tile_nunits_.p, p.tile_perm = tile_vals_[1].p, p.tile_stage_cap = tile_stage_cap_;
+    p.tile_units = tile_units_.p, p.tile_n_units = tile_nunits_.p, p.tile_perm = tile_vals_[1].p, p.tile_order = tile_by_size_ ? tile_order_.p : nullptr, p.tile_stage_cap = tile_stage_cap_;
     p.tile_unit_part = tile_unit_part_.p, p.tile_group_cnt = tile_group_cnt_.p;
     p.tile_ctl = tile_ctl_.p, p.tile_fill = 0;
 }

@@ -166,7 +166,12 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     // makes exactly one failing fetch per iteration, so the block that finishes the iteration advances it by n_units + gridDim.x.
     // (A block that is scheduled so late that the base has already advanced wraps around and leaves without a unit.)
     const uint32_t fetch_base = __ldcg(p.tile_ctl + 32);
-    auto fetch_unit = [&]() -> uint32_t { return atomicAdd(p.tile_ctl, 1u) - fetch_base; };  // thread 0 only
+    // Hand-out order: largest units first (tile_sort.cu), so that what a block picks up last is small.  The order only schedules:
+    // every unit's sums go to the unit's own slot.
+    auto fetch_unit = [&]() -> uint32_t {  // thread 0 only
+        const uint32_t t = atomicAdd(p.tile_ctl, 1u) - fetch_base;
+        return (t < n_units && p.tile_order != nullptr) ? p.tile_order[t] : t;
+    };
     // development timeline: thread 0 adds the time since its previous stamp to phase k (the block barriers align the warps)
     unsigned long long t_last = 0;
     if (p.dbg && threadIdx.x == 0) {

@@ -11,6 +11,7 @@
 //   tile_heads_kernel   unit boundaries: aligned chunks of 128 positions, cut where the next cell would not fit the unit's region
 //                       (gather also counts the heads per 1024-position tile)
 //   tile_units_kernel   compaction of the heads into units[0..n_units], units[n_units] = n
+//   tile_order_kernel   hand-out order of the units: by descending size
 #include <cub/device/device_radix_sort.cuh>
 
 #include "device_sort.cuh"
@@ -172,6 +173,34 @@ __global__ void __launch_bounds__(256) tile_units_kernel(const uint8_t *__restri
     }
 }
 
+// Hand-out order of the units: large ones first.  A block works through two or three units per iteration; whatever is handed out
+// last sets the length of the iteration, so it should be the cheap units (a handful of queries in a far, sparse cell), not a full
+// one.  Counting sort by size, one block; the order inside a size class is whatever the atomics give — it only schedules, every
+// unit's sums go to the unit's own slot.
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__restrict__ units, const uint32_t *__restrict__ n_units_p,
+                                                          uint32_t *__restrict__ order) {
+    __shared__ uint32_t s_bin[kUnitQueries + 2];
+    const uint32_t n_units = *n_units_p;
+    for (uint32_t b = threadIdx.x; b < kUnitQueries + 2; b += blockDim.x) s_bin[b] = 0;
+    __syncthreads();
+    auto bin_of = [&](uint32_t u) {
+        const uint32_t size = units[u + 1] - units[u];
+        return kUnitQueries - (size < (uint32_t)kUnitQueries ? size : (uint32_t)kUnitQueries);  // 0 = full units ... kUnitQueries = empty
+    };
+    for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) atomicAdd(&s_bin[bin_of(u)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t b = 0; b <= kUnitQueries; ++b) {
+            const uint32_t c = s_bin[b];
+            s_bin[b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) order[atomicAdd(&s_bin[bin_of(u)], 1u)] = u;
+}
+
 void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess, bool apply_guess) {
     static_assert(kUnitQueries <= 128, "a unit is one pass of a tile block");
     const uint32_t n32 = (uint32_t)n;
@@ -204,6 +233,8 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
     SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, tile_flag_.p, tile_vals_[1].p, src_.p,
                 tile_heads_.p);
     SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_flag_.p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);
+    tile_order_.ensure(n + 2);
+    SAGE_LAUNCH(tile_order_kernel, 1, 1024, 0, stream_, tile_units_.p, tile_nunits_.p, tile_order_.p);
 }
 
 }  // namespace sage

@@ -188,7 +188,7 @@ private:
     size_t persistent_max_ = 0;  // scans up to this many queries run the whole GN loop in one cooperative launch
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
     // tile search
-    DevBuf<uint32_t> tile_keys_[2], tile_vals_[2], tile_units_, tile_heads_, tile_nunits_;
+    DevBuf<uint32_t> tile_keys_[2], tile_vals_[2], tile_units_, tile_heads_, tile_nunits_, tile_order_;
     DevBuf<uint8_t> tile_tmp_, tile_flag_;  // sort scratch; unit-head flag per sorted position
     DevBuf<double> tile_unit_part_;      // [unit][17] sums of one unit
     DevBuf<uint32_t> tile_group_cnt_;    // units of a group that have published their sums
@@ -198,6 +198,7 @@ private:
     size_t tile_min_ = 0;          // scans of at least this many queries take the tile search (0 = never)
     uint32_t tile_stage_cap_ = 0;  // staging area of a block, in 16-byte records
     bool tile_persistent_ = true;  // whole GN loop in one cooperative launch
+    bool tile_by_size_ = true;     // hand the units out largest first
     size_t tile_fill_ = 1;         // 1: thinly spread query sets go to the per-query kernel (tile_units_too_thin); 0: never
     bool tile_units_too_thin(uint32_t n_units, size_t n) const;
     uint32_t last_units_ = 0;      // units of the last sorted scan

@@ -17,11 +17,11 @@ CONFIGS = {
     "tile_minb4_stage2560": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "4", "SAGE_TILE_STAGE": "2560"},
     "tile_minb5_stage1024": {"SAGE_TILE_MIN": "1", "SAGE_TILE_MINB": "5", "SAGE_TILE_STAGE": "1024"},
     "tile_stage2048": {"SAGE_TILE_MIN": "1", "SAGE_TILE_STAGE": "2048"},
-    "tile_no_heavy_first": {"SAGE_TILE_MIN": "1", "SAGE_TILE_HEAVY": "0"},
+    "tile_list_order": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BY_SIZE": "0"},
     "tile_blocks4": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "4"},
     "tile_blocks3": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "3"},
 }
-KEYS = ("SAGE_TILE", "SAGE_TILE_HEAVY", "SAGE_TILE_FILL", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS")
+KEYS = ("SAGE_TILE", "SAGE_TILE_BY_SIZE", "SAGE_TILE_FILL", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS")
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CONFIGS)
 sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2000, 8000, 15000, 30000, 60000, 120000]
 n_map = int(sys.argv[3]) if len(sys.argv) > 3 else 5_000_000

@@ -69,6 +69,7 @@ struct IterParams {
     unsigned long long xchg_tag;
     unsigned long long xchg_timeout_ns;  // how long the last block waits for the slowest rank before it gives up (comm_error)
     int light_probes;  // neighbour probes a query may spend in the thread-per-query phase before it is deferred
+    int step_everywhere;  // persistent kernels, single rank: every block reduces the partials and takes the step (LoopState)
     // tile search (search_tile.cuh): unit boundaries in the sorted query array [n_units + 1], their number (device scalar), and
     // the capacity of the block's staging area in 16-byte records
     const uint32_t *tile_units, *tile_n_units, *tile_perm;  // tile_perm: sorted position -> index in the caller's array
@@ -168,7 +169,8 @@ __device__ __forceinline__ Pose load_pose_cg(const Pose *q) {
 // The step is a chain of dependent f64 operations (two divisions, sqrt, sin/cos, atan2: ~8 us in one thread), so the independent
 // pieces run side by side in two warps: [solve] -> [rotation part of exp | translation part of exp] -> [pose product | log norm]
 // -> [stop test; the final pose only when the loop ends].  Same formulas, same operation order as pose_exp / pose_log.
-__device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
+// Pure part of the step: sums -> estimate (*s_pose) and |log(estimate)| (*s_norm), nothing but shared memory touched.
+__device__ __forceinline__ void icp_step_local(const double *sums, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
     __shared__ double s_xi[6];
     if (threadIdx.x == 0) {
         double xi[6];
@@ -215,12 +217,7 @@ __device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums,
     }
     __syncthreads();
     if (dbg && threadIdx.x == 0) dbg[6] = gtime();
-    if (threadIdx.x == 0) {
-        const Pose est = *s_pose;
-        st->est = est;
-        st->T_icp = pose_mul(est, load_pose_cg(&st->T_icp));
-        st->iter = __ldcg(&st->iter) + 1;
-    } else if (threadIdx.x == 32) {
+    if (threadIdx.x == 32) {
         double lg[6];
         pose_log(*s_pose, lg);
         double n2 = 0;
@@ -228,6 +225,16 @@ __device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums,
         for (int i = 0; i < 6; ++i) n2 += lg[i] * lg[i];
         *s_norm = sqrt(n2);
     }
+}
+// bookkeeping of one step in the device-resident state (thread 0, beside the log of icp_step_local in thread 32)
+__device__ __forceinline__ void icp_step_commit(IcpState *st, const Pose &est) {
+    st->est = est;
+    st->T_icp = pose_mul(est, load_pose_cg(&st->T_icp));
+    st->iter = __ldcg(&st->iter) + 1;
+}
+__device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
+    icp_step_local(sums, s_pose, s_norm, dbg);
+    if (threadIdx.x == 0) icp_step_commit(st, *s_pose);
     __syncthreads();
     if (threadIdx.x == 0) {
         st->last_norm = *s_norm;
@@ -533,6 +540,52 @@ __device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s
     }
 }
 
+// Adds the `count` partials of each of the 17 sums in a fixed order (partials[k * count + i]): warp w owns sums w, w+W, w+2W, ...;
+// lane l adds partials l, l+32, ... of each in order, then a fixed butterfly — the same tree for a given count, so results are
+// reproducible.  The loads of all the sums a warp owns are issued together (one round trip per 32 partials instead of one per sum).
+// Result in s_sums (shared) and, if given, in `out` (global).  Called by every thread of the block; no barrier inside.
+__device__ __forceinline__ void reduce_partials(const double *partials, uint32_t count, double *s_sums, double *out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
+    constexpr int kMaxOwn = (kSums + 1) / 2;  // >= ceil(kSums / kWarps) for kWarps >= 2 (blocks have at least 64 threads)
+    double v[kMaxOwn];
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) v[i] = 0.0;
+#pragma unroll 2
+    for (uint32_t b = lane; b < count; b += 32) {
+        double a[kMaxOwn];
+#pragma unroll
+        for (int i = 0; i < kMaxOwn; ++i) {
+            const int k = warp + kWarps * i;
+            a[i] = k < kSums ? __ldcg(partials + (size_t)k * count + b) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxOwn; ++i) v[i] += a[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) {
+        const int k = warp + kWarps * i;
+        if (k < kSums) {  // warp-uniform
+            double t = v[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) {
+                s_sums[k] = t;
+                if (out) out[k] = t;
+            }
+        }
+    }
+}
+
+// State a persistent kernel keeps on chip when EVERY block takes the Gauss-Newton step (single rank): the current estimate, the
+// iteration count and the stop flag never travel through global memory between iterations.
+struct LoopState {
+    Pose est;       // transform the next iteration applies to the queries
+    Pose T_icp;     // block 0 only: the accumulated estimate
+    double norm, est_th;
+    double sums[kSums];
+    int it, done;
+};
+
 // ---------------------------------------------------------------------------------------------
 // The part of an iteration that ONE block runs once every partial sum is published: add the `count` partials of each sum in a
 // fixed order (p.partials[k * count + i]), exchange the sums with the other ranks (fused peer-memory all-reduce, `tag` = this
@@ -540,39 +593,9 @@ __device__ __forceinline__ void flush_warp_batch(const IterParams &p, double (*s
 __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t count, Pose &s_est, double &s_norm, unsigned long long tag) {
     __shared__ double s_sums[kSums];  // the reduced sums stay on chip for the solve (st->sums is the copy the host / the exchange reads)
     IcpState *st = p.st;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
     __threadfence();
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * gridDim.x] = gtime();
-    // this block adds the partials: warp w owns sums w, w+W, w+2W, ...; lane l adds partials l, l+32, ... of each in order, then a
-    // fixed butterfly — the same tree for a given count, so results are reproducible.  The loads of all the sums a warp owns are
-    // issued together (one round trip per 32 partials instead of one per sum).
-    {
-        constexpr int kMaxOwn = (kSums + 1) / 2;  // >= ceil(kSums / kWarps) for kWarps >= 2 (blocks have at least 64 threads)
-        double v[kMaxOwn];
-#pragma unroll
-        for (int i = 0; i < kMaxOwn; ++i) v[i] = 0.0;
-#pragma unroll 2
-        for (uint32_t b = lane; b < count; b += 32) {
-            double a[kMaxOwn];
-#pragma unroll
-            for (int i = 0; i < kMaxOwn; ++i) {
-                const int k = warp + kWarps * i;
-                a[i] = k < kSums ? __ldcg(p.partials + (size_t)k * count + b) : 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < kMaxOwn; ++i) v[i] += a[i];
-        }
-#pragma unroll
-        for (int i = 0; i < kMaxOwn; ++i) {
-            const int k = warp + kWarps * i;
-            if (k < kSums) {  // warp-uniform
-                double t = v[i];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                if (lane == 0) st->sums[k] = t, s_sums[k] = t;
-            }
-        }
-    }
+    reduce_partials(p.partials, count, s_sums, st->sums);
     __syncthreads();
     if (p.xchg_world > 1) {
         // All-reduce of the 17 sums fused into this kernel: every rank's last block stores its sums, then the launch's tag,
@@ -635,10 +658,11 @@ __device__ __forceinline__ void reduce_and_step(const IterParams &p, uint32_t co
 // (COLS columns, a multiple of 32), publish the block's partials, elect the last block to finish, which runs reduce_and_step.
 template <int COLS>
 __device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s_acc)[COLS], Pose &s_est, double &s_norm, int &s_last,
-                                                 unsigned long long tag) {
+                                                 unsigned long long tag, double *publish_only = nullptr) {
     static_assert(COLS % 32 == 0, "whole warps of columns");
     IcpState *st = p.st;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kWarps = blockDim.x >> 5;
+    double *partials = publish_only ? publish_only : p.partials;
     // per-block partial sums: threads (fixed tree per sum) -> blocks (fixed order, by the last block to finish)
     __syncthreads();
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x + 3] = gtime();
@@ -649,10 +673,11 @@ __device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) {
-            p.partials[(size_t)k * gridDim.x + blockIdx.x] = v;  // [sum][block]
+            partials[(size_t)k * gridDim.x + blockIdx.x] = v;  // [sum][block]
             __threadfence();
         }
     }
+    if (publish_only) return;  // the caller's grid barrier orders the partials; every block reduces them itself
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
     __syncthreads();
@@ -670,7 +695,7 @@ __device__ __forceinline__ void finish_iteration(const IterParams &p, double (*s
 // cross-section of the scan and the expensive regions (sparse, far from the sensor) spread over all SMs.
 #define SAGE_STAMP(i) do { if (p.dbg && pass == 0 && warp == 0) { __syncwarp(); if (lane == 0) p.dbg[kDbg * blockIdx.x + (i)] = gtime(); } } while (0)
 template <bool COUNT>
-__device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
+__device__ __forceinline__ void nn_search_iteration(const IterParams &p, const Pose *est_in = nullptr, double *publish_only = nullptr) {
     constexpr int kWarps = kNnThreads / 32;
     // per-thread running sums live in shared memory (s_acc[k][thread]) so that the search loop keeps its registers
     __shared__ double s_acc[kSums][kNnThreads];
@@ -681,8 +706,8 @@ __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
     __shared__ double s_norm;
     __shared__ int s_last;
     IcpState *st = p.st;
-    if (p.respect_done && __ldcg(&st->done)) return;
-    if (threadIdx.x == 0) s_est = load_pose_cg(&st->est);
+    if (est_in == nullptr && p.respect_done && __ldcg(&st->done)) return;
+    if (threadIdx.x == 0) s_est = est_in ? *est_in : load_pose_cg(&st->est);
     if (p.dbg && threadIdx.x == 0) p.dbg[kDbg * blockIdx.x] = gtime();
 #pragma unroll
     for (int k = 0; k < kSums; ++k) s_acc[k][threadIdx.x] = 0.0;
@@ -903,7 +928,7 @@ __device__ __forceinline__ void nn_search_iteration(const IterParams &p) {
             atomicAdd(&st->stat_heavy, n_heavy);
         }
     }
-    finish_iteration<kNnThreads>(p, s_acc, s_est, s_norm, s_last, p.xchg_tag);
+    finish_iteration<kNnThreads>(p, s_acc, s_est, s_norm, s_last, p.xchg_tag, publish_only);
 }
 
 template <bool COUNT>
@@ -915,8 +940,55 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
 // launch gap, no host poll between iterations.  Used for the small scans of the pipeline level, where an iteration is ~20 us
 // of work and the gaps were as long as the work (profiles/r01g_streaming.md).  Launched with cudaLaunchCooperativeKernel, which
 // refuses a grid that is not co-resident, so the barrier cannot deadlock.
+// End of an iteration when every block takes the step (persistent kernels, single rank): after the grid barrier that made the
+// partials of all blocks visible, each block adds them in the same fixed order, solves and exponentiates — identical bits in every
+// block — and keeps the new estimate on chip.  Block 0 also keeps the books the host reads at the end.  Compared with electing a last
+// block this takes the ticket, the serial reduction, the pose product and the reload of the estimate off every iteration's path
+// and saves the second grid-wide wait.
+__device__ __forceinline__ void loop_step_everywhere(const IterParams &p, LoopState &ls, const double *partials, uint32_t count, int max_iterations) {
+    reduce_partials(partials, count, ls.sums, nullptr);
+    __syncthreads();
+    icp_step_local(ls.sums, &ls.est, &ls.norm);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ls.T_icp = pose_mul(ls.est, ls.T_icp);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ls.it += 1;
+        ls.done = (ls.norm < ls.est_th || ls.it >= max_iterations) ? 1 : 0;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void loop_state_init(const IterParams &p, LoopState &ls) {
+    if (threadIdx.x == 0) {
+        ls.est = load_pose_cg(&p.st->est);
+        ls.T_icp = pose_identity();
+        ls.it = 0, ls.done = __ldcg(&p.st->done), ls.norm = 0, ls.est_th = p.st->est_th;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void loop_state_commit(const IterParams &p, const LoopState &ls) {  // block 0, after the loop
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    IcpState *st = p.st;
+    st->est = ls.est, st->T_icp = ls.T_icp, st->iter = ls.it, st->last_norm = ls.norm;
+    for (int k = 0; k < kSums; ++k) st->sums[k] = ls.sums[k];
+    if (ls.it > 0) st->result = pose_mul(ls.T_icp, st->guess);  // T_icp * guess, core/Registration.cpp:140
+    st->done = 1;
+}
+
 __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_persistent_kernel(IterParams p, int max_iterations, int first_apply) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    if (p.step_everywhere) {
+        __shared__ LoopState ls;
+        loop_state_init(p, ls);
+        while (!ls.done) {
+            p.apply_est = ls.it > 0 ? 1 : first_apply;  // first_apply = 0: the caller has already applied the initial guess
+            double *partials = p.partials + (size_t)(ls.it & 1) * kSums * gridDim.x;  // two buffers: a block may be one iteration ahead
+            nn_search_iteration<false>(p, &ls.est, partials);
+            grid.sync();
+            loop_step_everywhere(p, ls, partials, gridDim.x, max_iterations);
+        }
+        loop_state_commit(p, ls);
+        return;
+    }
     for (int i = 0; i < max_iterations; ++i) {
         p.apply_est = i > 0 ? 1 : first_apply;  // first_apply = 0: the caller has already applied the initial guess (tile_prepare)
         nn_search_iteration<false>(p);
@@ -1061,12 +1133,13 @@ void VoxelMapGPU::init_search_config() {
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
     tile_by_size_ = env_long("SAGE_TILE_BY_SIZE", 1) != 0;
+    step_everywhere_ = env_long("SAGE_STEP_EVERYWHERE", 1) != 0;
     tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 1);  // 0: the tile search never declines a thinly spread query set
     {
         const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
         xchg_timeout_ns_ = (unsigned long long)(t < 1 ? 1 : t) * 1000000000ull;
     }
-    partials_.ensure((size_t)kSums * (nn_grid_ > tile_grid_ ? nn_grid_ : tile_grid_));
+    partials_.ensure((size_t)2 * kSums * (nn_grid_ > tile_grid_ ? nn_grid_ : tile_grid_));  // two buffers (iteration parity)
 }
 
 // the rule by which nn_tile_iteration declines a query set (search_tile.cuh), for the paths that decide on the host
@@ -1095,7 +1168,7 @@ void VoxelMapGPU::fill_params(IterParams &p, double4 *src, size_t n, double max_
     }
     p.st = icp_.p, p.partials = partials_.p, p.tgt_out = tgt_out, p.matched_out = matched_out;
     p.dbg = nullptr;
-    p.light_probes = 8, p.all_warp = 0;
+    p.light_probes = 8, p.all_warp = 0, p.step_everywhere = 0;
     p.apply_est = (mode == 0), p.respect_done = (mode == 0);
     p.solve = (mode == 0 && comm_ == nullptr);  // NCCL path: all-reduce and solve are separate launches
     p.xchg_world = 1, p.xchg_rank = 0, p.xchg_tag = 0, p.xchg_timeout_ns = xchg_timeout_ns_;
@@ -1162,6 +1235,8 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     if (prof) prof_begin();
     if (persistent_iters > 0) {
         int first_apply = pre_transformed ? 0 : 1;
+        // every block takes the step itself (no elected last block) as long as re-reading the partials in every block is cheap
+        p.step_everywhere = (step_everywhere_ && peer_world_ <= 1 && comm_ == nullptr && grid <= 192) ? 1 : 0;
         void *args[] = {&p, &persistent_iters, &first_apply};
         SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1187,6 +1262,7 @@ void VoxelMapGPU::launch_tile(size_t n, double max_dist, double kernel, double s
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
     prof_begin();
     if (persistent_iters > 0) {
+        p.step_everywhere = (step_everywhere_ && peer_world_ <= 1 && comm_ == nullptr) ? 1 : 0;
         void *args[] = {&p, &persistent_iters};
         SAGE_CUDA(cudaLaunchCooperativeKernel(tile_kernel_ptr(tile_minb_, true), dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);

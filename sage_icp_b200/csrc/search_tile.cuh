@@ -129,17 +129,30 @@ __device__ __forceinline__ uint32_t tile_block_scan(TileShared &sh, uint32_t min
     return base;
 }
 
+// true (grid-uniformly) if this query set is left to the per-query kernel; sets the flag the host reads
+__device__ __forceinline__ bool tile_declines(const IterParams &p, uint32_t n_units) {
+    const unsigned long long rounds = (n_units + gridDim.x - 1) / gridDim.x;
+    const bool thin = p.tile_fill != 0 && rounds * 15000ull + 12000ull > 30000ull + (unsigned long long)p.n * 48ull / 100ull;
+    if (thin || __ldcg(&p.st->declined)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.st->declined = 1, p.st->done = 1;
+        return true;
+    }
+    return false;
+}
+
 // One Gauss-Newton iteration over the unit list.  `apply_est`: transform the queries by st->est first (every iteration but the
 // first: tile_sort.cu has applied the initial guess while sorting).  `phase`: parity of the block's mbarrier, carried across
 // iterations by the persistent kernel.
+// `ls` (persistent kernel, single rank): the loop state kept on chip — the estimate comes from there, group sums go to the partial
+// buffer of the iteration's parity, and nobody is elected to finish: every block takes the step after the caller's grid barrier.
 template <bool COUNT>
 __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShared &sh, float4 *stage, bool apply_est, uint32_t &phase,
-                                                  unsigned long long tag) {
+                                                  unsigned long long tag, const LoopState *ls = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const float INF = __int_as_float(0x7f800000);
     IcpState *st = p.st;
-    if (p.respect_done && __ldcg(&st->done)) return;
-    if (threadIdx.x == 0) sh.est = load_pose_cg(&st->est);
+    if (ls == nullptr && p.respect_done && __ldcg(&st->done)) return;
+    if (threadIdx.x == 0) sh.est = ls ? ls->est : load_pose_cg(&st->est);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double vs = p.voxel_size;
@@ -152,20 +165,14 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     // configs[4]'s uniform queries: one unit per query — is declined here, grid-uniformly and before anything is touched: the host
     // sees the flag at its next read-back and runs the per-query kernel on the (already sorted) array.  Deciding on the device keeps a
     // host round trip out of every ordinary registration.  tile_fill == 0: never decline (tests force a schedule).
-    {
-        const unsigned long long rounds = (n_units + gridDim.x - 1) / gridDim.x;
-        const bool thin = p.tile_fill != 0 && rounds * 15000ull + 12000ull > 30000ull + (unsigned long long)p.n * 48ull / 100ull;
-        if (thin || __ldcg(&st->declined)) {
-            if (blockIdx.x == 0 && threadIdx.x == 0) st->declined = 1, st->done = 1;
-            return;
-        }
-    }
+    if (ls == nullptr && tile_declines(p, n_units)) return;  // (the persistent kernel asks once, before its loop)
     const uint32_t n_groups = (n_units + kTileGroup - 1) / kTileGroup;
     // Units are handed out by a counter that only grows during a registration (p.tile_ctl[0], alone on its cache line: every
     // block hits it two or three times per iteration); p.tile_ctl[32] is its value at the start of this iteration — every block
     // makes exactly one failing fetch per iteration, so the block that finishes the iteration advances it by n_units + gridDim.x.
     // (A block that is scheduled so late that the base has already advanced wraps around and leaves without a unit.)
-    const uint32_t fetch_base = __ldcg(p.tile_ctl + 32);
+    const uint32_t fetch_base = ls ? (uint32_t)ls->it * (n_units + gridDim.x) : __ldcg(p.tile_ctl + 32);
+    double *group_partials = p.partials + (ls ? (size_t)(ls->it & 1) * kSums * n_groups : 0);
     // Hand-out order: largest units first (tile_sort.cu), so that what a block picks up last is small.  The order only schedules:
     // every unit's sums go to the unit's own slot.
     auto fetch_unit = [&]() -> uint32_t {  // thread 0 only
@@ -513,13 +520,13 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
             if (threadIdx.x < kSums) {
                 double v = 0;
                 for (uint32_t i = gfirst; i < gfirst + gsize; ++i) v += __ldcg(&p.tile_unit_part[(size_t)i * kSums + threadIdx.x]);
-                p.partials[(size_t)threadIdx.x * n_groups + g] = v;  // [sum][group]
+                group_partials[(size_t)threadIdx.x * n_groups + g] = v;  // [sum][group]
                 __threadfence();
             }
             __syncthreads();
             if (threadIdx.x == 0) {
                 p.tile_group_cnt[g] = 0;  // ready for the next iteration
-                sh.flag = (atomicAdd(&st->ticket, 1u) == n_groups - 1) ? 2 : 0;
+                sh.flag = (ls == nullptr && atomicAdd(&st->ticket, 1u) == n_groups - 1) ? 2 : 0;
             }
             __syncthreads();
             if (sh.flag == 2) {
@@ -571,6 +578,20 @@ __global__ void __launch_bounds__(kTileThreads, MINB) nn_tile_persistent_kernel(
     if (threadIdx.x == 0) mbar_init(smem_addr(&sh.mbar), kTileThreads);
     __syncthreads();
     uint32_t phase = 0;
+    if (p.step_everywhere) {  // single rank: every block takes the step, the loop state stays on chip (registration.cu)
+        __shared__ LoopState ls;
+        const uint32_t n_units = *p.tile_n_units;
+        if (tile_declines(p, n_units)) return;
+        const uint32_t n_groups = (n_units + kTileGroup - 1) / kTileGroup;
+        loop_state_init(p, ls);
+        while (!ls.done) {
+            nn_tile_iteration<false>(p, sh, s_tile_stage, ls.it > 0, phase, 0ull, &ls);
+            grid.sync();
+            loop_step_everywhere(p, ls, p.partials + (size_t)(ls.it & 1) * kSums * n_groups, n_groups, max_iterations);
+        }
+        loop_state_commit(p, ls);
+        return;
+    }
     for (int i = 0; i < max_iterations; ++i) {
         nn_tile_iteration<false>(p, sh, s_tile_stage, i > 0, phase, p.xchg_tag + (unsigned long long)i);
         grid.sync();

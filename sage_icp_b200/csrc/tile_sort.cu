@@ -218,7 +218,7 @@ void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess
     const size_t groups = (n + 1) / 16 + 2;
     tile_group_cnt_.ensure(groups);
     SAGE_CUDA(cudaMemsetAsync(tile_group_cnt_.p, 0, groups * sizeof(uint32_t), stream_));
-    if ((size_t)17 * groups > partials_.cap) partials_.ensure((size_t)17 * groups);
+    if ((size_t)2 * 17 * groups > partials_.cap) partials_.ensure((size_t)2 * 17 * groups);  // two buffers (iteration parity)
     tile_ctl_.ensure(64);
     SAGE_CUDA(cudaMemsetAsync(tile_ctl_.p, 0, 64 * sizeof(uint32_t), stream_));  // hand-out counter and base restart at 0
     const size_t tmp_bytes = sort_pairs_tmp_bytes_u32(n, kKeyBitsTile);

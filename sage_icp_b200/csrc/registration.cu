@@ -1133,7 +1133,7 @@ void VoxelMapGPU::init_search_config() {
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
     tile_by_size_ = env_long("SAGE_TILE_BY_SIZE", 1) != 0;
-    step_everywhere_ = env_long("SAGE_STEP_EVERYWHERE", 1) != 0;
+    step_everywhere_ = (int)env_long("SAGE_STEP_EVERYWHERE", 1);  // 0 never, 1 where it pays (large tiled scans), 2 wherever possible
     tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 1);  // 0: the tile search never declines a thinly spread query set
     {
         const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
@@ -1235,8 +1235,9 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     if (prof) prof_begin();
     if (persistent_iters > 0) {
         int first_apply = pre_transformed ? 0 : 1;
-        // every block takes the step itself (no elected last block) as long as re-reading the partials in every block is cheap
-        p.step_everywhere = (step_everywhere_ && peer_world_ <= 1 && comm_ == nullptr && grid <= 192) ? 1 : 0;
+        // every block taking the step itself (no elected last block) does not pay here: measured 28.4 vs 28.3 us per iteration at
+        // 700 queries, 38.3 vs 37.9 at 2 000 (profiles/r02_tile_kernel.md); SAGE_STEP_EVERYWHERE=2 forces it (tests)
+        p.step_everywhere = (step_everywhere_ == 2 && peer_world_ <= 1 && comm_ == nullptr && grid <= 192) ? 1 : 0;
         void *args[] = {&p, &persistent_iters, &first_apply};
         SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1262,7 +1263,9 @@ void VoxelMapGPU::launch_tile(size_t n, double max_dist, double kernel, double s
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
     prof_begin();
     if (persistent_iters > 0) {
-        p.step_everywhere = (step_everywhere_ && peer_world_ <= 1 && comm_ == nullptr) ? 1 : 0;
+        // every block takes the step itself after ONE grid barrier: pays for large scans (69.8 vs 73.7 us per iteration at 120 k
+        // queries), not for small ones (52.3 vs 51.0 at 15 k: 592 blocks re-reading the partials outweigh the saved election)
+        p.step_everywhere = (peer_world_ <= 1 && comm_ == nullptr && (step_everywhere_ == 2 || (step_everywhere_ == 1 && n >= 65536))) ? 1 : 0;
         void *args[] = {&p, &persistent_iters};
         SAGE_CUDA(cudaLaunchCooperativeKernel(tile_kernel_ptr(tile_minb_, true), dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);

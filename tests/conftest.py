@@ -37,16 +37,16 @@ def pytest_collection_modifyitems(config, items):
 SEARCH_MODES = {
     "default": {},                                                              # tile search from 12 288 queries up
     # tile search forced for every size and density (SAGE_TILE_FILL=0 switches off the "units must be well filled" rule)
-    "tile": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0"},                                      # persistent loop, 96 registers
+    "tile": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0", "SAGE_STEP_EVERYWHERE": "2"},         # persistent loop, every block steps
     "tile_launch": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0", "SAGE_TILE_PERSISTENT": "0", "SAGE_TILE_MINB": "8", "SAGE_TILE_STAGE": "704"},
     "tile_spill": {"SAGE_TILE_MIN": "1", "SAGE_TILE_FILL": "0", "SAGE_TILE_STAGE": "96", "SAGE_TILE_MINB": "4"},  # staging too small: global scans
-    "legacy": {"SAGE_TILE": "0"},                                               # thread-per-query + deferred warp phase only
+    "legacy": {"SAGE_TILE": "0", "SAGE_STEP_EVERYWHERE": "2"},                  # per-query kernel only, every block steps
 }
 
 
 @pytest.fixture(params=list(SEARCH_MODES))
 def search_mode(request, monkeypatch):
-    for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
+    for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS", "SAGE_STEP_EVERYWHERE"):
         monkeypatch.delenv(k, raising=False)
     for k, v in SEARCH_MODES[request.param].items():
         monkeypatch.setenv(k, v)

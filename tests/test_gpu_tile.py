@@ -14,7 +14,7 @@ BASIC_LABELS = [40, 44, 48, 49, 50, 70, 72]
 def _maps(orc, pts, monkeypatch=None, env=None):
     import sage_icp_b200 as sg
     if env is not None:
-        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS"):
+        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS", "SAGE_STEP_EVERYWHERE"):
             monkeypatch.delenv(k, raising=False)
         if env.get("SAGE_TILE") != "0":
             monkeypatch.setenv("SAGE_TILE_FILL", "0")  # the tile search whatever the density (these tests are about ITS results)
@@ -72,7 +72,8 @@ def test_tile_registration_equals_legacy_and_is_reproducible(orc, monkeypatch):
     o.add_points(pts)
     pose_o, it_o = o.register_frame_core(scan, guess, 3.0, 1.0 / 3.0, 0.4, threads=8)
     out = {}
-    for name, env in (("tile", {}), ("tile_launch_per_iteration", {"SAGE_TILE_PERSISTENT": "0"}), ("legacy", {"SAGE_TILE": "0"})):
+    for name, env in (("tile", {"SAGE_STEP_EVERYWHERE": "0"}), ("tile_every_block_steps", {"SAGE_STEP_EVERYWHERE": "2"}),
+                      ("tile_launch_per_iteration", {"SAGE_TILE_PERSISTENT": "0"}), ("legacy", {"SAGE_TILE": "0"})):
         g = _maps(orc, pts, monkeypatch, env)
         p1, it1 = g.register_frame(scan, guess, 3.0, 1.0 / 3.0, 0.4)
         p2, it2 = g.register_frame(scan, guess, 3.0, 1.0 / 3.0, 0.4)
@@ -81,6 +82,7 @@ def test_tile_registration_equals_legacy_and_is_reproducible(orc, monkeypatch):
         assert it1 == it_o and dt <= POSE_TOL_M and da <= POSE_TOL_RAD, (name, it1, it_o, dt, da)
         out[name] = p1
     assert np.array_equal(out["tile"], out["tile_launch_per_iteration"])  # one cooperative launch == one launch per iteration
+    assert np.array_equal(out["tile"], out["tile_every_block_steps"])     # ... == every block taking the step itself
     dt, da = pose_delta(out["tile"], out["legacy"])
     assert dt <= 1e-9 and da <= 1e-10, (dt, da)  # different summation trees only
 

@@ -177,4 +177,36 @@ struct IcpState {
     unsigned long long stat_staged;  // tile search: records pulled into shared memory by bulk copies
 };
 
+// Arguments of the once-per-registration kernels of the tile search (tile_sort.cu) that change from call to call.  They live in
+// device memory (one small H2D copy per registration) instead of the kernels' parameter lists, so that the captured CUDA graph of
+// those kernels can be replayed unchanged for every scan of the same size.
+struct TilePrepArgs {
+    Pose guess;           // initial guess (TransformPoints(initial_guess, source), core/Registration.cpp:122)
+    const double4 *frame; // the caller's scan
+    double est_th;        // ESTIMATION_THRESHOLD_
+    int max_iters;        // MAX_NUM_ITERATIONS_
+    int apply;            // 1: transform by `guess` while sorting; 0: plain gather (correspondence-only entry points)
+};
+
+#ifdef __CUDACC__
+// start of a registration (core/Registration.cpp:113-126): estimate = guess, T_icp = identity, counters cleared
+__device__ __forceinline__ void icp_state_init(IcpState *st, const Pose &guess, int max_iters, double est_th) {
+    st->est = guess;
+    st->T_icp = pose_identity();
+    st->guess = guess;
+    st->result = guess;
+    for (int i = 0; i < 17; ++i) st->sums[i] = 0;
+    st->last_norm = 0;
+    st->est_th = est_th;
+    st->max_iters = max_iters;
+    st->iter = 0;
+    st->done = (max_iters <= 0);
+    st->ticket = 0;
+    st->stat_occupied = st->stat_candidates = 0;
+    st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = st->stat_staged = 0;
+    st->comm_error = 0;
+    st->declined = 0;
+}
+#endif
+
 }  // namespace sage

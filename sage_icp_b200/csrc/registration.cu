@@ -170,13 +170,23 @@ __device__ __forceinline__ Pose load_pose_cg(const Pose *q) {
 // pieces run side by side in two warps: [solve] -> [rotation part of exp | translation part of exp] -> [pose product | log norm]
 // -> [stop test; the final pose only when the loop ends].  Same formulas, same operation order as pose_exp / pose_log.
 // Pure part of the step: sums -> estimate (*s_pose) and |log(estimate)| (*s_norm), nothing but shared memory touched.
-__device__ __forceinline__ void icp_step_local(const double *sums, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
+__device__ __forceinline__ void icp_step_local(const double *sums, Pose *s_pose, double *s_norm, double est_th, unsigned long long *dbg = nullptr) {
     __shared__ double s_xi[6];
+    __shared__ int s_need_log;
     if (threadIdx.x == 0) {
         double xi[6];
         icp_solve_xi(sums, xi);
 #pragma unroll
         for (int i = 0; i < 6; ++i) s_xi[i] = xi[i];
+        // The stop test needs |log(exp(xi))| (core/Registration.cpp:137).  For a rotation below 1 rad that IS |xi| up to the rounding
+        // of the exp / log round trip (< 1e-13 relative), and pose_log — atan2, a square root, three divisions in one dependent f64
+        // chain — was the longest piece of the step (3.3-4.4 us of 10, profiles/r02_tile_kernel.md).  So the test is made on |xi|
+        // whenever |xi| is further than 1e-9 (relative) from the threshold, where both norms fall on the same side of it; only a step
+        // that lands within that sliver of the threshold (or a non-finite / large-rotation one) still takes the full logarithm below.
+        const double n = sqrt((xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]) + (xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]));
+        const double th2 = (xi[3] * xi[3] + xi[4] * xi[4]) + xi[5] * xi[5];
+        *s_norm = n;
+        s_need_log = (th2 < 1.0 && fabs(n - est_th) > 1e-9 * fmax(n, est_th)) ? 0 : 1;
         if (dbg) dbg[5] = gtime();
     }
     __syncthreads();
@@ -217,7 +227,7 @@ __device__ __forceinline__ void icp_step_local(const double *sums, Pose *s_pose,
     }
     __syncthreads();
     if (dbg && threadIdx.x == 0) dbg[6] = gtime();
-    if (threadIdx.x == 32) {
+    if (s_need_log && threadIdx.x == 32) {
         double lg[6];
         pose_log(*s_pose, lg);
         double n2 = 0;
@@ -233,7 +243,7 @@ __device__ __forceinline__ void icp_step_commit(IcpState *st, const Pose &est) {
     st->iter = __ldcg(&st->iter) + 1;
 }
 __device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
-    icp_step_local(sums, s_pose, s_norm, dbg);
+    icp_step_local(sums, s_pose, s_norm, st->est_th, dbg);
     if (threadIdx.x == 0) icp_step_commit(st, *s_pose);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -245,23 +255,7 @@ __device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums,
     }
 }
 
-__global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double est_th) {
-    st->est = guess;
-    st->T_icp = pose_identity();
-    st->guess = guess;
-    st->result = guess;
-    for (int i = 0; i < kSums; ++i) st->sums[i] = 0;
-    st->last_norm = 0;
-    st->est_th = est_th;
-    st->max_iters = max_iters;
-    st->iter = 0;
-    st->done = (max_iters <= 0);
-    st->ticket = 0;
-    st->stat_occupied = st->stat_candidates = 0;
-    st->stat_scanned = st->stat_probes = st->stat_exact = st->stat_heavy = st->stat_staged = 0;
-    st->comm_error = 0;
-    st->declined = 0;
-}
+__global__ void icp_init_kernel(IcpState *st, Pose guess, int max_iters, double est_th) { icp_state_init(st, guess, max_iters, est_th); }
 
 __global__ void icp_solve_kernel(IcpState *st) {  // <<<1, 64>>>, after the NCCL all-reduce of the sums
     __shared__ Pose s_pose;
@@ -948,7 +942,7 @@ __global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_kernel(
 __device__ __forceinline__ void loop_step_everywhere(const IterParams &p, LoopState &ls, const double *partials, uint32_t count, int max_iterations) {
     reduce_partials(partials, count, ls.sums, nullptr);
     __syncthreads();
-    icp_step_local(ls.sums, &ls.est, &ls.norm);
+    icp_step_local(ls.sums, &ls.est, &ls.norm, ls.est_th);
     if (blockIdx.x == 0 && threadIdx.x == 0) ls.T_icp = pose_mul(ls.est, ls.T_icp);
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -974,7 +968,11 @@ __device__ __forceinline__ void loop_state_commit(const IterParams &p, const Loo
     st->done = 1;
 }
 
-__global__ void __launch_bounds__(kNnThreads, SAGE_LIGHT_MINB) nn_search_persistent_kernel(IterParams p, int max_iterations, int first_apply) {
+// MINB: resident blocks per SM the register allocation aims at.  A pipeline-level cloud (a few hundred to ~2 000 queries, a warp
+// each) fills at most two blocks per SM, so it runs the instantiation with 128 registers per thread: the 64-register one spills
+// ~4 KB per thread (ptxas -v), and local-memory round trips sit on the dependent chain of every query.
+template <int MINB>
+__global__ void __launch_bounds__(kNnThreads, MINB) nn_search_persistent_kernel(IterParams p, int max_iterations, int first_apply) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     if (p.step_everywhere) {
         __shared__ LoopState ls;
@@ -1103,9 +1101,17 @@ void VoxelMapGPU::init_search_config() {
     int coop = 0;
     SAGE_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_));
     int per_sm_p = 0;
-    SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, nn_search_persistent_kernel, kNnThreads, 0));
+    SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, nn_search_persistent_kernel<SAGE_LIGHT_MINB>, kNnThreads, 0));
     persistent_grid_ = sm_count_ * per_sm_p;
     if (persistent_grid_ > nn_grid_) persistent_grid_ = nn_grid_;
+    {
+        int per_sm_w = 0;
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, nn_search_persistent_kernel<2>, kNnThreads, 0));
+        const long wide = env_long("SAGE_SMALL_WIDE", 2);  // 0: always the 64-register instantiation, 1: 128 where it fits, 2: 255 / 128
+        persistent_grid_wide_ = wide != 0 ? sm_count_ * per_sm_w : 0;
+        SAGE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w, nn_search_persistent_kernel<1>, kNnThreads, 0));
+        persistent_grid_widest_ = wide >= 2 ? sm_count_ * (per_sm_w > 1 ? 1 : per_sm_w) : 0;
+    }
     if (persistent_grid_ < 1) coop = 0;
     coop_ok_ = coop != 0;
     persistent_max_ = coop ? 20000 : 0;  // scans up to this many queries run their GN loop in one cooperative launch
@@ -1135,6 +1141,7 @@ void VoxelMapGPU::init_search_config() {
     tile_by_size_ = env_long("SAGE_TILE_BY_SIZE", 1) != 0;
     step_everywhere_ = (int)env_long("SAGE_STEP_EVERYWHERE", 1);  // 0 never, 1 where it pays (large tiled scans), 2 wherever possible
     tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 1);  // 0: the tile search never declines a thinly spread query set
+    tile_graph_ = env_long("SAGE_TILE_GRAPH", 1) != 0;   // sort + unit list replayed as a captured CUDA graph (tile_sort.cu)
     {
         const long t = env_long("SAGE_XCHG_TIMEOUT_S", 30);
         xchg_timeout_ns_ = (unsigned long long)(t < 1 ? 1 : t) * 1000000000ull;
@@ -1239,7 +1246,10 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
         // 700 queries, 38.3 vs 37.9 at 2 000 (profiles/r02_tile_kernel.md); SAGE_STEP_EVERYWHERE=2 forces it (tests)
         p.step_everywhere = (step_everywhere_ == 2 && peer_world_ <= 1 && comm_ == nullptr && grid <= 192) ? 1 : 0;
         void *args[] = {&p, &persistent_iters, &first_apply};
-        SAGE_CUDA(cudaLaunchCooperativeKernel((const void *)nn_search_persistent_kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
+        const void *kernel = grid <= (uint32_t)persistent_grid_widest_ ? (const void *)nn_search_persistent_kernel<1>
+                             : grid <= (uint32_t)persistent_grid_wide_ ? (const void *)nn_search_persistent_kernel<2>
+                                                                       : (const void *)nn_search_persistent_kernel<SAGE_LIGHT_MINB>;
+        SAGE_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kNnThreads), args, 0, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);
     } else if (mode == 2) {
         SAGE_LAUNCH(nn_search_kernel<true>, grid, kNnThreads, 0, stream_, p);
@@ -1302,7 +1312,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     bool tile = tile_min_ > 0 && n >= tile_min_;
     bool sorted = false;
     if (tile) {
-        tile_prepare(frame, n, guess, true);
+        tile_prepare(frame, n, guess, true, true, max_iters, est_th);  // ... and the loop state initialised (icp_state_init)
         sorted = true;  // src_ = the queries in cell order, initial guess applied
         // A query set spread thinly over the map is declined by the kernel itself (`declined` below, search_tile.cuh).  Only the NCCL
         // variant decides here, with a read-back of the unit count: its all-reduce launches must match on every rank.
@@ -1316,7 +1326,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
     } else if (n) {
         SAGE_CUDA(cudaMemcpyAsync(src_.p, frame, n * sizeof(double4), cudaMemcpyDeviceToDevice, stream_));
     }
-    SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, guess, max_iters, est_th);
+    if (!sorted) SAGE_LAUNCH(icp_init_kernel, 1, 1, 0, stream_, icp_.p, guess, max_iters, est_th);
     // iterations are launched in batches (kernels of a finished registration return at once) and `done` is polled between
     // batches; the first batch is sized from the previous registration so that the common case needs one round trip
     int launched = 0;

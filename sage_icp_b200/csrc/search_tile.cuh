@@ -499,6 +499,38 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
         // ---- I: publish the unit's sums; the block that completes a group adds it; the one that completes the last group steps ------
         const uint32_t g = u / kTileGroup;
         const uint32_t gfirst = g * kTileGroup, gsize = min((uint32_t)kTileGroup, n_units - gfirst);
+        if (ls != nullptr) {
+            // Every block takes the step itself (persistent loop, single rank): nobody has to be elected, so warp 0 publishes the unit —
+            // and, when it completes a group, adds the group — on its own while the other warps start on the next unit; it catches
+            // up at that unit's first barrier (phase A takes them about as long as the publish takes warp 0).  The columns it reads are
+            // rewritten only in phase H of the next unit, several block barriers later; the caller's grid barrier orders the group sums.
+            if (threadIdx.x == 0) sh.unit = next_unit;
+            __syncthreads();  // every warp has written its columns; the next unit is known to all
+            if (warp == 0) {
+                if (lane < kSums) {
+                    double v = 0;
+#pragma unroll 8
+                    for (int c = 0; c < kTileCols; ++c) v += sh.acc[lane][c];
+                    p.tile_unit_part[(size_t)u * kSums + lane] = v;
+                    __threadfence();
+                }
+                __syncwarp();
+                uint32_t last = 0;
+                if (lane == 0) last = (atomicAdd(&p.tile_group_cnt[g], 1u) == gsize - 1) ? 1u : 0u;
+                last = __shfl_sync(FULL, last, 0);
+                if (last) {
+                    __threadfence();
+                    if (lane < kSums) {
+                        double v = 0;
+                        for (uint32_t i = gfirst; i < gfirst + gsize; ++i) v += __ldcg(&p.tile_unit_part[(size_t)i * kSums + lane]);
+                        group_partials[(size_t)lane * n_groups + g] = v;  // [sum][group]
+                    }
+                    if (lane == 0) p.tile_group_cnt[g] = 0;  // ready for the next iteration
+                }
+            }
+            if (p.dbg && threadIdx.x == 0) sh.dbg_t[10] += 1, sh.dbg_t[11] += uend - ubeg;
+            continue;
+        }
         __syncthreads();  // every warp has written its columns
         if (warp == 0) {  // one warp publishes (lane k adds the 32 columns of sum k in order); the others go and wait at the barrier
             if (lane < kSums) {

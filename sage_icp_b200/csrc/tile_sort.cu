@@ -52,13 +52,17 @@ constexpr int kKeyBitsTile = 2 * kCellBitsXY + kCellBitsZ + 3;
 constexpr int kUnitQueries = 128;  // = kTileThreads of search_tile.cuh (checked in registration.cu)
 constexpr int kHeadTile = 1024;    // positions per block of the head count / compaction kernels
 
-__global__ void tile_key_kernel(const double4 *__restrict__ frame, uint32_t n, Pose guess, int apply, double vs, uint32_t *__restrict__ keys,
-                                uint32_t *__restrict__ vals) {
+__global__ void tile_key_kernel(const TilePrepArgs *__restrict__ a, uint32_t n, double vs, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                uint32_t *__restrict__ group_cnt, uint32_t n_group_cnt, uint32_t *__restrict__ ctl) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // the per-group arrival counters and the unit hand-out counter of the tile kernel restart at 0 (the counters reset themselves at
+    // the end of every iteration; this covers a registration that was abandoned half way)
+    for (uint32_t j = i; j < n_group_cnt; j += gridDim.x * blockDim.x) group_cnt[j] = 0;
+    if (i < 64) ctl[i] = 0;
     if (i >= n) return;
-    const double4 s = frame[i];
+    const double4 s = a->frame[i];
     double x = s.x, y = s.y, z = s.z;
-    if (apply) pose_act(guess, s.x, s.y, s.z, x, y, z);
+    if (a->apply) pose_act(a->guess, s.x, s.y, s.z, x, y, z);
     // cell = voxel >> 1 (arithmetic shift = floor), 8 + 8 + 5 bits, then the voxel inside the cell: queries that share a home
     // voxel are neighbours in the order, so a warp's home-bucket scan is converged
     const int vx = trunc_div(x, vs), vy = trunc_div(y, vs), vz = trunc_div(z, vs);
@@ -109,12 +113,15 @@ __global__ void tile_heads_kernel(const uint32_t *__restrict__ keys, uint32_t n,
     }
 }
 
-__global__ void __launch_bounds__(256) tile_gather_kernel(const double4 *__restrict__ frame, uint32_t n, Pose guess, int apply,
-                                                          const uint8_t *__restrict__ head, const uint32_t *__restrict__ perm,
-                                                          double4 *__restrict__ src, uint32_t *__restrict__ tile_heads) {
+__global__ void __launch_bounds__(256) tile_gather_kernel(const TilePrepArgs *__restrict__ a, uint32_t n, const uint8_t *__restrict__ head,
+                                                          const uint32_t *__restrict__ perm, double4 *__restrict__ src,
+                                                          uint32_t *__restrict__ tile_heads) {
     __shared__ uint32_t s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
+    const double4 *__restrict__ frame = a->frame;
+    const int apply = a->apply;
+    const Pose guess = a->guess;
     uint32_t heads = 0;
     for (uint32_t e = 0; e < kHeadTile / 256; ++e) {
         const uint32_t j = blockIdx.x * kHeadTile + e * 256 + threadIdx.x;
@@ -178,8 +185,10 @@ __global__ void __launch_bounds__(256) tile_units_kernel(const uint8_t *__restri
 // one.  Counting sort by size, one block; the order inside a size class is whatever the atomics give — it only schedules, every
 // unit's sums go to the unit's own slot.
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__restrict__ units, const uint32_t *__restrict__ n_units_p,
-                                                          uint32_t *__restrict__ order) {
+                                                          uint32_t *__restrict__ order, IcpState *st, const TilePrepArgs *__restrict__ a) {
     __shared__ uint32_t s_bin[kUnitQueries + 2];
+    // the registration's device-resident loop state starts here too (st != null: a registration, not a correspondence-only call)
+    if (st != nullptr && threadIdx.x == 0) icp_state_init(st, a->guess, a->max_iters, a->est_th);
     const uint32_t n_units = *n_units_p;
     for (uint32_t b = threadIdx.x; b < kUnitQueries + 2; b += blockDim.x) s_bin[b] = 0;
     __syncthreads();
@@ -201,40 +210,107 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__rest
     for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) order[atomicAdd(&s_bin[bin_of(u)], 1u)] = u;
 }
 
-void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess, bool apply_guess) {
-    static_assert(kUnitQueries <= 128, "a unit is one pass of a tile block");
+// The kernels of tile_prepare, enqueued on stream_ (directly, or into a stream capture).  Every buffer is sized by the caller.
+int VoxelMapGPU::tile_prepare_enqueue(size_t n, bool with_init) {
     const uint32_t n32 = (uint32_t)n;
+    const uint32_t tiles = (n32 + kHeadTile - 1) / kHeadTile;
+    const size_t groups = (n + 1) / 16 + 2;
+    SAGE_LAUNCH(tile_key_kernel, (n32 + 255) / 256, 256, 0, stream_, prep_args_.p, n32, voxel_size_, tile_keys_[0].p, tile_vals_[0].p, tile_group_cnt_.p,
+                (uint32_t)groups, tile_ctl_.p);
+    const int sort_launches = sort_pairs_u32(tile_tmp_.p, tile_tmp_bytes_, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, n, kKeyBitsTile, stream_);
+    g_launches.fetch_add(sort_launches, std::memory_order_relaxed);
+    const uint32_t chunks = (n32 + kUnitQueries - 1) / kUnitQueries;
+    SAGE_LAUNCH(tile_heads_kernel, (chunks + 7) / 8, 256, 0, stream_, tile_keys_[1].p, n32, tile_flag_.p);  // one warp per chunk
+    SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, prep_args_.p, n32, tile_flag_.p, tile_vals_[1].p, src_.p, tile_heads_.p);
+    SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_flag_.p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);
+    SAGE_LAUNCH(tile_order_kernel, 1, 1024, 0, stream_, tile_units_.p, tile_nunits_.p, tile_order_.p, with_init ? icp_.p : (IcpState *)nullptr,
+                prep_args_.p);
+    return 5 + sort_launches;
+}
+
+void VoxelMapGPU::tile_graph_drop() {
+    if (prep_exec_) cudaGraphExecDestroy(prep_exec_);
+    prep_exec_ = nullptr;
+    prep_key_.clear();
+}
+
+// Sort + unit list (+ the start of the loop state when `with_init`: registrations) of one scan.  The ~10 launches are short (3-12 us
+// each), so enqueueing them costs the host more than running them costs the device — ~90 us of an 880 us registration were the
+// device waiting for the next launch.  The second time a scan of the same size arrives with the same buffers, the launches are
+// captured into a CUDA graph (the per-call arguments live in device memory: TilePrepArgs), and from then on a registration
+// enqueues one small copy and one graph.  SAGE_TILE_GRAPH=0 keeps the plain launches; any failure of the capture does too.
+void VoxelMapGPU::tile_prepare(const double4 *frame, size_t n, const Pose &guess, bool apply_guess, bool with_init, int max_iters, double est_th) {
+    static_assert(kUnitQueries <= 128, "a unit is one pass of a tile block");
     for (int k = 0; k < 2; ++k) {
         tile_keys_[k].ensure(n);
         tile_vals_[k].ensure(n);
     }
     tile_units_.ensure(n + 2);
-    const uint32_t tiles = (n32 + kHeadTile - 1) / kHeadTile;
+    const uint32_t tiles = ((uint32_t)n + kHeadTile - 1) / kHeadTile;
     tile_heads_.ensure(tiles + 1);
     tile_nunits_.ensure(1);
-    // per-unit sums and per-group arrival counters of the two-level reduction (search_tile.cuh); the counters reset themselves at
-    // the end of every iteration, the memset only covers a registration that was abandoned half way (an error)
+    // per-unit sums and per-group arrival counters of the two-level reduction (search_tile.cuh)
     tile_unit_part_.ensure((n + 1) * 17);
     const size_t groups = (n + 1) / 16 + 2;
     tile_group_cnt_.ensure(groups);
-    SAGE_CUDA(cudaMemsetAsync(tile_group_cnt_.p, 0, groups * sizeof(uint32_t), stream_));
     if ((size_t)2 * 17 * groups > partials_.cap) partials_.ensure((size_t)2 * 17 * groups);  // two buffers (iteration parity)
     tile_ctl_.ensure(64);
-    SAGE_CUDA(cudaMemsetAsync(tile_ctl_.p, 0, 64 * sizeof(uint32_t), stream_));  // hand-out counter and base restart at 0
-    const size_t tmp_bytes = sort_pairs_tmp_bytes_u32(n, kKeyBitsTile);
-    tile_tmp_.ensure(tmp_bytes ? tmp_bytes : 1);
-    SAGE_LAUNCH(tile_key_kernel, (n32 + 255) / 256, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, voxel_size_, tile_keys_[0].p,
-                tile_vals_[0].p);
-    g_launches.fetch_add(sort_pairs_u32(tile_tmp_.p, tmp_bytes, tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p, tile_vals_[1].p, n, kKeyBitsTile, stream_),
-                         std::memory_order_relaxed);
+    if (n != tile_tmp_n_) tile_tmp_bytes_ = sort_pairs_tmp_bytes_u32(n, kKeyBitsTile), tile_tmp_n_ = n;
+    tile_tmp_.ensure(tile_tmp_bytes_ ? tile_tmp_bytes_ : 1);
     tile_flag_.ensure(n);
-    const uint32_t chunks = (n32 + kUnitQueries - 1) / kUnitQueries;
-    SAGE_LAUNCH(tile_heads_kernel, (chunks + 7) / 8, 256, 0, stream_, tile_keys_[1].p, n32, tile_flag_.p);  // one warp per chunk
-    SAGE_LAUNCH(tile_gather_kernel, tiles, 256, 0, stream_, frame, n32, guess, apply_guess ? 1 : 0, tile_flag_.p, tile_vals_[1].p, src_.p,
-                tile_heads_.p);
-    SAGE_LAUNCH(tile_units_kernel, tiles, 256, 0, stream_, tile_flag_.p, n32, tile_heads_.p, tile_units_.p, tile_nunits_.p);
     tile_order_.ensure(n + 2);
-    SAGE_LAUNCH(tile_order_kernel, 1, 1024, 0, stream_, tile_units_.p, tile_nunits_.p, tile_order_.p);
+    icp_.ensure(1);
+    prep_args_.ensure(1);
+    prep_pin_.ensure(1);
+    // the pinned slot is free: every caller synchronises the stream before it returns
+    *prep_pin_.p = TilePrepArgs{guess, frame, est_th, max_iters, apply_guess ? 1 : 0};
+    SAGE_CUDA(cudaMemcpyAsync(prep_args_.p, prep_pin_.p, sizeof(TilePrepArgs), cudaMemcpyHostToDevice, stream_));
+
+    if (!tile_graph_) {
+        tile_prepare_enqueue(n, with_init);
+        return;
+    }
+    // what a captured graph has baked in: the size, the variant and every buffer it touches
+    const std::vector<const void *> key = {(const void *)n, (const void *)(size_t)(with_init ? 1 : 0), tile_keys_[0].p, tile_keys_[1].p, tile_vals_[0].p,
+                                           tile_vals_[1].p, tile_units_.p, tile_heads_.p, tile_nunits_.p, tile_group_cnt_.p, tile_ctl_.p, tile_tmp_.p,
+                                           tile_flag_.p, tile_order_.p, src_.p, icp_.p, prep_args_.p};
+    if (prep_exec_ != nullptr && key == prep_key_) {
+        SAGE_CUDA(cudaGraphLaunch(prep_exec_, stream_));
+        g_launches.fetch_add(prep_kernel_nodes_, std::memory_order_relaxed);
+        return;
+    }
+    if (key != prep_seen_) {  // first sight of this size / these buffers: plain launches, remember it
+        tile_graph_drop();
+        prep_seen_ = key;
+        tile_prepare_enqueue(n, with_init);
+        return;
+    }
+    // second sight: capture, instantiate, launch
+    tile_graph_drop();
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(stream_, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+        try {
+            prep_kernel_nodes_ = tile_prepare_enqueue(n, with_init);
+            g_launches.fetch_sub(prep_kernel_nodes_, std::memory_order_relaxed);  // captured, not run yet
+        } catch (const CudaError &) {
+            ok = false;
+        }
+        if (cudaStreamEndCapture(stream_, &graph) != cudaSuccess || graph == nullptr) ok = false;
+    }
+    if (ok && cudaGraphInstantiate(&prep_exec_, graph, 0) != cudaSuccess) ok = false, prep_exec_ = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    if (ok && cudaGraphLaunch(prep_exec_, stream_) != cudaSuccess) ok = false;
+    if (ok) {
+        prep_key_ = key;
+        g_launches.fetch_add(prep_kernel_nodes_, std::memory_order_relaxed);
+        return;
+    }
+    // the capture did not work here: clear the error, never try again, launch plainly
+    cudaGetLastError();
+    tile_graph_drop();
+    tile_graph_ = false;
+    tile_prepare_enqueue(n, with_init);
 }
 
 }  // namespace sage

@@ -334,6 +334,7 @@ VoxelMapGPU::~VoxelMapGPU() {
     if (stream_) cudaStreamSynchronize(stream_);
     comm_destroy();
     peer_detach();
+    tile_graph_drop();
     if (xchg_local_) cudaFree(xchg_local_);
     for (auto &e : prof_events_) {
         cudaEventDestroy(e.first);

@@ -136,7 +136,10 @@ private:
                      uint8_t *matched_out);
     // tile search (search_tile.cuh, tile_sort.cu): sort + unit list once per registration, then one launch per iteration or one
     // cooperative launch for the whole loop
-    void tile_prepare(const double4 *frame, size_t n, const Pose &guess, bool apply_guess);
+    void tile_prepare(const double4 *frame, size_t n, const Pose &guess, bool apply_guess, bool with_init = false, int max_iters = 0,
+                      double est_th = 0.0);
+    int tile_prepare_enqueue(size_t n, bool with_init);  // returns the kernels launched
+    void tile_graph_drop();
     void launch_tile(size_t n, double max_dist, double kernel, double sem_th, int iter_index, int persistent_iters);
     void prof_begin();
     void prof_end(int iterations);
@@ -185,6 +188,7 @@ private:
     int nn_grid_ = 0;
     size_t all_warp_max_ = 0;  // scans up to this many queries use the warp-per-query mode
     int persistent_grid_ = 0;    // co-resident blocks of the persistent kernel
+    int persistent_grid_wide_ = 0, persistent_grid_widest_ = 0;  // ... of its 128- and 255-register instantiations (small scans)
     size_t persistent_max_ = 0;  // scans up to this many queries run the whole GN loop in one cooperative launch
     int last_iters_ = 0;  // iterations of the previous registration (sizes the first launch batch)
     // tile search
@@ -204,6 +208,14 @@ private:
     bool tile_units_too_thin(uint32_t n_units, size_t n) const;
     uint32_t last_units_ = 0;      // units of the last sorted scan
     PinBuf<uint32_t> tile_nunits_pin_;
+    // per-call arguments of the sort / unit-list kernels (device copy + pinned source) and the captured graph of those kernels
+    DevBuf<TilePrepArgs> prep_args_;
+    PinBuf<TilePrepArgs> prep_pin_;
+    bool tile_graph_ = true;              // SAGE_TILE_GRAPH=0: plain launches
+    cudaGraphExec_t prep_exec_ = nullptr;
+    std::vector<const void *> prep_key_, prep_seen_;  // what the graph has baked in / what the previous plain call looked like
+    long long prep_kernel_nodes_ = 0;
+    size_t tile_tmp_bytes_ = 0, tile_tmp_n_ = (size_t)-1;
     bool coop_ok_ = false;
     int light_probes_ = -1;  // < 0: chosen from the number of queries (launch_iteration); SAGE_LIGHT_PROBES overrides
     bool dbg_on_ = false;

@@ -14,7 +14,7 @@ BASIC_LABELS = [40, 44, 48, 49, 50, 70, 72]
 def _maps(orc, pts, monkeypatch=None, env=None):
     import sage_icp_b200 as sg
     if env is not None:
-        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS", "SAGE_STEP_EVERYWHERE"):
+        for k in ("SAGE_TILE", "SAGE_TILE_MIN", "SAGE_TILE_FILL", "SAGE_TILE_PERSISTENT", "SAGE_TILE_STAGE", "SAGE_TILE_MINB", "SAGE_TILE_BLOCKS", "SAGE_STEP_EVERYWHERE", "SAGE_TILE_GRAPH"):
             monkeypatch.delenv(k, raising=False)
         if env.get("SAGE_TILE") != "0":
             monkeypatch.setenv("SAGE_TILE_FILL", "0")  # the tile search whatever the density (these tests are about ITS results)
@@ -130,3 +130,37 @@ def test_tile_handles_empty_ragged_and_degenerate_inputs(orc, monkeypatch):
     assert np.array_equal(matched[ok], m_o) and np.array_equal(tgt[ok][m_o], tgt_o)
     for th in (0.0, -1.0, 2.5):
         _check_corr(g, o, q[ok], 1.5, th)
+
+
+def test_captured_prep_graph_equals_plain_launches(orc, monkeypatch):
+    """The sort + unit-list kernels of a registration are captured into a CUDA graph the second time a scan of the same size arrives
+    and replayed from then on (tile_sort.cu).  Different scans and guesses of one size, a different size in between (the graph is
+    dropped and rebuilt), host and device-resident entry points: every pose must carry the bits of the plain launches."""
+    import torch
+    from sage_icp_b200 import synthetic as syn
+    pts = _street()
+    scans = [syn.make_scan(s, (0.4 * s, 0.0, 0.0), n_beams=64, n_az=500) for s in range(4)]
+    guesses = [syn.pose7_from_xyyaw((0.4 * s + 0.2, -0.1 + 0.05 * s, 0.01 * (s - 1))) for s in range(4)]
+    small = syn.make_scan(9, (0.0, 0.0, 0.0), n_beams=64, n_az=300)
+    order = [0, 1, 2, 3, "small", "small", 3, 2, 1, 0]
+    out = {}
+    for name, env in (("graph", {}), ("plain", {"SAGE_TILE_GRAPH": "0"})):
+        g = _maps(orc, pts, monkeypatch, env)
+        poses = []
+        for k in order:
+            if k == "small":
+                poses.append(g.register_frame(small, guesses[0], 3.0, 1.0 / 3.0, 0.4, 8, 0.0))
+            elif k % 2:  # scan resident in device memory (the frame pointer changes from call to call)
+                d = torch.from_numpy(scans[k]).cuda()
+                poses.append(g.register_frame_device(d.data_ptr(), len(scans[k]), guesses[k], 3.0, 1.0 / 3.0, 0.4, 8, 0.0))
+                del d
+            else:
+                poses.append(g.register_frame(scans[k], guesses[k], 3.0, 1.0 / 3.0, 0.4, 8, 0.0))
+        out[name] = poses
+    for (pg, ig), (pp, ip) in zip(out["graph"], out["plain"]):
+        assert ig == ip and np.array_equal(np.asarray(pg), np.asarray(pp))
+    o = orc.OracleMap(0.8, 1e9, 20, 20, BASIC_LABELS, evict_faithful=False)
+    o.add_points(pts)
+    pose_o, it_o = o.register_frame_core(scans[3], guesses[3], 3.0, 1.0 / 3.0, 0.4, threads=8, max_iters=8, est_th=0.0)
+    dt, da = pose_delta(np.asarray(out["graph"][3][0]), pose_o)
+    assert out["graph"][3][1] == it_o and dt <= POSE_TOL_M and da <= POSE_TOL_RAD

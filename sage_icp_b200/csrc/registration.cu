@@ -236,20 +236,30 @@ __device__ __forceinline__ void icp_step_local(const double *sums, Pose *s_pose,
         *s_norm = sqrt(n2);
     }
 }
-// bookkeeping of one step in the device-resident state (thread 0, beside the log of icp_step_local in thread 32)
-__device__ __forceinline__ void icp_step_commit(IcpState *st, const Pose &est) {
-    st->est = est;
-    st->T_icp = pose_mul(est, load_pose_cg(&st->T_icp));
-    st->iter = __ldcg(&st->iter) + 1;
-}
+// One step on the device-resident state, by the block that finishes an iteration.  What thread 0 needs from global memory for the
+// bookkeeping — the accumulated estimate, the iteration count, the limits — is requested before the solve, so that the ~1 us of each
+// of those loads passes during it instead of after it (they were a chain of three round trips behind the step: 3.3 us of 7.4).
 __device__ __forceinline__ void icp_step_block(IcpState *st, const double *sums, Pose *s_pose, double *s_norm, unsigned long long *dbg = nullptr) {
-    icp_step_local(sums, s_pose, s_norm, st->est_th, dbg);
-    if (threadIdx.x == 0) icp_step_commit(st, *s_pose);
+    Pose T_prev = pose_identity();
+    int it_prev = 0, max_it = 0;
+    if (threadIdx.x == 0) {
+        T_prev = load_pose_cg(&st->T_icp);
+        it_prev = __ldcg(&st->iter);
+        max_it = st->max_iters;
+    }
+    const double est_th = st->est_th;  // constant during a registration
+    icp_step_local(sums, s_pose, s_norm, est_th, dbg);
+    if (threadIdx.x == 0) {  // beside the (rare) log of icp_step_local in thread 32
+        st->est = *s_pose;
+        T_prev = pose_mul(*s_pose, T_prev);  // T_icp = est * T_icp, core/Registration.cpp:135
+        st->T_icp = T_prev;
+        st->iter = it_prev + 1;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         st->last_norm = *s_norm;
-        if (*s_norm < st->est_th || st->iter >= st->max_iters) {
-            st->result = pose_mul(st->T_icp, st->guess);  // T_icp * guess (core/Registration.cpp:140): needed once, when the loop ends
+        if (*s_norm < est_th || it_prev + 1 >= max_it) {
+            st->result = pose_mul(T_prev, st->guess);  // T_icp * guess (core/Registration.cpp:140): needed once, when the loop ends
             st->done = 1;
         }
     }
@@ -1242,9 +1252,12 @@ void VoxelMapGPU::launch_iteration(double4 *src, size_t n, double max_dist, doub
     if (prof) prof_begin();
     if (persistent_iters > 0) {
         int first_apply = pre_transformed ? 0 : 1;
-        // every block taking the step itself (no elected last block) does not pay here: measured 28.4 vs 28.3 us per iteration at
-        // 700 queries, 38.3 vs 37.9 at 2 000 (profiles/r02_tile_kernel.md); SAGE_STEP_EVERYWHERE=2 forces it (tests)
-        p.step_everywhere = (step_everywhere_ == 2 && peer_world_ <= 1 && comm_ == nullptr && grid <= 192) ? 1 : 0;
+        // every block takes the step itself (no elected last block, loop state on chip): with the wide instantiations it pays —
+        // 16.2 vs 19.2 us per iteration at 700 queries, 23.9 vs 24.8 at 2 100, 29.1 vs 30.0 at 5 000 — but not on the full grid of
+        // the 64-register one (12 000 queries, 375 blocks each re-reading 375 x 17 partials: 58.0 vs 53.2; profiles/
+        // r02w_small_scans.md).  SAGE_STEP_EVERYWHERE=0 keeps the elected block, =2 forces every block.
+        p.step_everywhere = (peer_world_ <= 1 && comm_ == nullptr &&
+                             (step_everywhere_ == 2 || (step_everywhere_ == 1 && grid <= (uint32_t)persistent_grid_wide_))) ? 1 : 0;
         void *args[] = {&p, &persistent_iters, &first_apply};
         const void *kernel = grid <= (uint32_t)persistent_grid_widest_ ? (const void *)nn_search_persistent_kernel<1>
                              : grid <= (uint32_t)persistent_grid_wide_ ? (const void *)nn_search_persistent_kernel<2>

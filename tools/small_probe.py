@@ -7,7 +7,10 @@ import numpy as np
 import sage_icp_b200 as sg
 import bench
 
-VARIANTS = {"wide2 (255/128/64 regs)": {}, "wide1 (128/64)": {"SAGE_SMALL_WIDE": "1"}, "wide0 (64)": {"SAGE_SMALL_WIDE": "0"}}
+VARIANTS = {"default (255/128/64 regs, every block steps)": {}, "elected last block": {"SAGE_STEP_EVERYWHERE": "0"},
+            "wide1 (128/64)": {"SAGE_SMALL_WIDE": "1"}, "wide0 (64)": {"SAGE_SMALL_WIDE": "0"}}
+if os.environ.get("SMALL_PROBE_VARIANTS"):
+    VARIANTS = {k: v for k, v in VARIANTS.items() if any(k.startswith(w) for w in os.environ["SMALL_PROBE_VARIANTS"].split(","))}
 sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [300, 700, 1100, 2100, 5000, 12000]
 n_map = 1_000_000
 half = bench.street_half_length(n_map)
@@ -15,6 +18,7 @@ pts = bench.make_map_points(n_map)
 scan, guess = bench.make_queries(0, 64, 1875, half)
 for name, env in VARIANTS.items():
     os.environ.pop("SAGE_SMALL_WIDE", None)
+    os.environ.pop("SAGE_STEP_EVERYWHERE", None)
     os.environ.update(env)
     m = sg.SageMap(0.8, 1e9, 20, 20, bench.BASIC_LABELS)
     m.add_points(pts)
@@ -35,6 +39,7 @@ for name, env in VARIANTS.items():
 
 import ctypes as C
 os.environ.pop("SAGE_SMALL_WIDE", None)
+os.environ.pop("SAGE_STEP_EVERYWHERE", None)
 m = sg.SageMap(0.8, 1e9, 20, 20, bench.BASIC_LABELS)
 m.add_points(pts)
 L = sg.load_library(); L.sage_debug_timeline.restype = C.c_size_t

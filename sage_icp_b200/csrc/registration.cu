@@ -1286,9 +1286,10 @@ void VoxelMapGPU::launch_tile(size_t n, double max_dist, double kernel, double s
     const size_t smem = (size_t)tile_stage_cap_ * sizeof(float4);
     prof_begin();
     if (persistent_iters > 0) {
-        // every block takes the step itself after ONE grid barrier: pays for large scans (69.8 vs 73.7 us per iteration at 120 k
-        // queries), not for small ones (52.3 vs 51.0 at 15 k: 592 blocks re-reading the partials outweigh the saved election)
-        p.step_everywhere = (peer_world_ <= 1 && comm_ == nullptr && (step_everywhere_ == 2 || (step_everywhere_ == 1 && n >= 65536))) ? 1 : 0;
+        // every block takes the step itself after ONE grid barrier, and warp 0 publishes a unit while the other warps start the next:
+        // 69.0 vs 72.7 us per iteration at 120 k queries, 60.8 vs 61.2 at 60 k, 50.0 vs 50.6 at 15 k (visit Z, same box; before the
+        // publish moved off the block's path it had lost below 65 536 queries)
+        p.step_everywhere = (peer_world_ <= 1 && comm_ == nullptr && step_everywhere_ >= 1) ? 1 : 0;
         void *args[] = {&p, &persistent_iters};
         SAGE_CUDA(cudaLaunchCooperativeKernel(tile_kernel_ptr(tile_minb_, true), dim3(tile_grid_), dim3(kTileThreads), args, smem, stream_));
         g_launches.fetch_add(1, std::memory_order_relaxed);

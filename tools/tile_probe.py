@@ -20,8 +20,10 @@ CONFIGS = {
     "tile_list_order": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BY_SIZE": "0"},
     "tile_blocks4": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "4"},
     "tile_blocks3": {"SAGE_TILE_MIN": "1", "SAGE_TILE_BLOCKS": "3"},
+    "tile_elected": {"SAGE_TILE_MIN": "1", "SAGE_STEP_EVERYWHERE": "0"},
+    "tile_every_block": {"SAGE_TILE_MIN": "1", "SAGE_STEP_EVERYWHERE": "2"},
 }
-KEYS = ("SAGE_TILE", "SAGE_TILE_BY_SIZE", "SAGE_TILE_FILL", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS")
+KEYS = ("SAGE_TILE", "SAGE_TILE_BY_SIZE", "SAGE_TILE_FILL", "SAGE_TILE_MIN", "SAGE_TILE_PERSISTENT", "SAGE_TILE_MINB", "SAGE_TILE_STAGE", "SAGE_TILE_BLOCKS", "SAGE_STEP_EVERYWHERE")
 which = sys.argv[1].split(",") if len(sys.argv) > 1 else list(CONFIGS)
 sizes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [2000, 8000, 15000, 30000, 60000, 120000]
 n_map = int(sys.argv[3]) if len(sys.argv) > 3 else 5_000_000

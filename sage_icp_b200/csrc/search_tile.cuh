@@ -196,13 +196,12 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
     } while (0)
     unsigned long long n_ranked = 0, n_probes = 0, n_exact = 0, n_pooled = 0, n_staged = 0;  // work counters (COUNT launches only)
 
-    uint32_t next_unit = 0;  // thread 0: the unit after the current one, fetched while the current one is being worked on
+    uint32_t next_unit = 0;  // thread 0: the unit after the current one, drawn while the current one is being finished
     if (threadIdx.x == 0) sh.unit = fetch_unit();
     __syncthreads();
     for (;;) {
         const uint32_t u = sh.unit;  // set before the last barrier
         if (u >= n_units) break;
-        if (threadIdx.x == 0) next_unit = fetch_unit();  // its latency hides behind phase A
         TILE_STAMP(8);
         const uint32_t ubeg = p.tile_units[u], uend = p.tile_units[u + 1];  // at most kTileThreads queries by construction
         const uint32_t q = ubeg + threadIdx.x;
@@ -453,6 +452,12 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
             }
         }
         TILE_STAMP(6);
+        // The next unit is drawn HERE, not at the top of the loop: a draw is a claim, and claims made at the start of a unit go to the
+        // blocks that started first — which hold the largest units (hand-out order) — instead of the blocks that finish first.  With
+        // fewer units than twice the grid (a 15 000-query shard of an 8-GPU run: ~700 units on 592 blocks) the eager draw gave the
+        // blocks with a full unit a second one while two thirds of the grid idled (31 us to the last unit where one full unit takes
+        // 17: profiles/r02w_small_scans.md §6).  Phase H's record fetch still hides the atomic's round trip.
+        if (threadIdx.x == 0) next_unit = fetch_unit();
         // ---- H: acceptance on the exact records, residual, weight, the 16 sums + pair count -----------------------------------------
         {
             double a[kSums];

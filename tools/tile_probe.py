@@ -71,6 +71,9 @@ if os.environ.get("TILE_TIMELINE", "1") != "0":
     m = sg.SageMap(0.8, 1e9, 20, 20, bench.BASIC_LABELS)
     m.add_points(pts)
     L = sg.load_library(); L.sage_debug_timeline.restype = C.c_size_t
+    if os.environ.get("TILE_TIMELINE_N"):
+        tn = int(os.environ["TILE_TIMELINE_N"])
+        scan = np.ascontiguousarray(scan[:: len(scan) // tn][:tn])
     m.register_frame(scan, guess, 3.0, 1 / 3, 0.4, max_iters=2, est_th=0.0)
     n = L.sage_debug_timeline(m.h, None, C.c_size_t(0))
     m.register_frame(scan, guess, 3.0, 1 / 3, 0.4, max_iters=3, est_th=0.0)

@@ -36,6 +36,19 @@ extern std::atomic<long long> g_launches;  // every kernel launch of this librar
         SAGE_CUDA(cudaGetLastError());                             \
     } while (0)
 
+// CUDA loads a kernel's code the first time it is launched (lazy module loading, the default since CUDA 12.2).  On a live drive
+// that is a stall in the middle of a frame: the first registration whose query count needs another instantiation of the search
+// kernel took 150-500 ms on a fresh B200 box (profiles/r02w_small_scans.md §7).  Every translation unit therefore names its kernels
+// once, when a map / front end is created on a device: cudaFuncGetAttributes loads the function.
+inline void preload_kernel(const void *k) {
+    cudaFuncAttributes a;
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) cudaGetLastError();  // a hint: never an error of the caller
+}
+void preload_registration_kernels();
+void preload_tile_sort_kernels();
+void preload_voxel_map_kernels();
+void preload_frontend_kernels();
+
 // ---------------------------------------------------------------------------------------------
 // growable device / pinned-host buffers
 template <class T>

@@ -8,6 +8,9 @@
 // the map insertion order, so it is reproduced exactly: the distinct keys' 20-bit hashes go to the host in
 // first-index order, robin_iteration_order() replays the table, and the permutation comes back for the gather.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "frontend.cuh"
 #include "device_sort.cuh"
@@ -26,12 +29,13 @@ void robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out
     if (n >= (1u << 28)) throw ArgError("robin_iteration_order: too many keys");
     constexpr uint64_t kEmpty = ~0ull;
     constexpr int kDistLimit = 8192;
-    static thread_local std::vector<uint64_t> buf[2];
+    static thread_local std::vector<uint64_t> buf[2], live_buf;
     size_t final_cap = 2;
     while (final_cap < 2 * n) final_cap *= 2;
     final_cap *= 2;  // a probe-length-forced growth (hash saturation) may add one generation
     for (auto &b : buf)
         if (b.size() < final_cap) b.resize(final_cap);
+    if (live_buf.size() < n + 1) live_buf.resize(n + 1);
     uint64_t *cur = buf[0].data(), *nxt = buf[1].data();
     size_t B = 0, mask = 0, size = 0, load_threshold = 0;
     bool grow_next = false;
@@ -61,11 +65,24 @@ void robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out
         if (count > final_cap) throw ArgError("robin_iteration_order: table growth beyond the preallocated generations");
         std::fill(nxt, nxt + count, kEmpty);
         const size_t nmask = count - 1;
-        for (size_t b = 0; b < B; ++b)
-            if (cur[b] != kEmpty) {
-                const uint64_t rest = cur[b] & 0xffffffffffffull;
-                place(nxt, nmask, (size_t)(rest >> 28) & nmask, 0, rest, false);
-            }
+        // The replay is bound by branch mispredictions, not by memory (every table fits the host's L2): whether a bucket of a
+        // half-full table is occupied is a coin toss.  So the live entries are first compacted in bucket order WITHOUT a branch,
+        // and an element whose new ideal bucket is still free — the common case right after doubling — is stored without entering
+        // the swap-and-carry loop (1.5x on the whole function, 56 -> 38 ns per key on fresh keys).
+        uint64_t *live = live_buf.data();
+        size_t n_live = 0;
+        for (size_t b = 0; b < B; ++b) {
+            live[n_live] = cur[b];
+            n_live += (cur[b] != kEmpty);
+        }
+        for (size_t j = 0; j < n_live; ++j) {
+            const uint64_t rest = live[j] & 0xffffffffffffull;
+            const size_t ib = (size_t)(rest >> 28) & nmask;
+            if (nxt[ib] == kEmpty)
+                nxt[ib] = rest;  // distance 0
+            else
+                place(nxt, nmask, ib, 0, rest, false);
+        }
         std::swap(cur, nxt);
         B = count, mask = nmask;
         load_threshold = (size_t)((float)count * 0.5f);
@@ -90,7 +107,7 @@ void robin_iteration_order(const uint32_t *hash20, size_t n, uint32_t *order_out
     }
     size_t k = 0;
     for (size_t b = 0; b < B; ++b)
-        if (cur[b] != kEmpty) order_out[k++] = (uint32_t)(cur[b] & 0xfffffffu);
+        if (cur[b] != kEmpty) order_out[k++] = (uint32_t)(cur[b] & 0xfffffffu);  // (order_out holds exactly n entries: no branchless overrun)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -479,8 +496,20 @@ __global__ void deskew_kernel(const double4 *in, const double *ts, uint32_t n, d
 // host
 
 FrontEnd::FrontEnd(const GroupTable &groups, int device, cudaStream_t stream) : groups_(groups), device_(device), stream_(stream) {
+    SAGE_CUDA(cudaSetDevice(device_));
+    preload_frontend_kernels();
     total_.ensure(2);
     total_pin_.ensure(2);
+    if (const char *e = getenv("SAGE_FE_TRACE")) trace_ = atoi(e) != 0;
+}
+
+FrontEnd::~FrontEnd() {
+    if (trace_ && n_calls_ > 0)
+        fprintf(stderr,
+                "[sage front end] %lld VoxelDownsample calls, %.1f distinct keys per call; host us per call: enqueue %.1f, wait for the device %.1f, "
+                "group split %.1f, robin replay %.1f, permutation + gather launch %.1f\n",
+                n_calls_, (double)n_keys_ / n_calls_, 1e6 * t_enqueue_ / n_calls_, 1e6 * t_wait_ / n_calls_, 1e6 * t_group_ / n_calls_,
+                1e6 * t_replay_ / n_calls_, 1e6 * t_tail_ / n_calls_);
 }
 
 void FrontEnd::scan_flags(size_t n, uint32_t *total_out, const uint32_t *err) {
@@ -524,6 +553,8 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
     perm_pin_[parity_].ensure(n);  // this buffer's last reader (two calls ago) finished before the previous call's synchronisation
     uint32_t *perm_host = perm_pin_[parity_].p;
     parity_ ^= 1;
+    using fe_clock = std::chrono::steady_clock;
+    const auto tr0 = fe_clock::now();
     SAGE_CUDA(cudaMemsetAsync(total_.p, 0, 2 * sizeof(uint32_t), stream_));
     SAGE_CUDA(cudaMemsetAsync(tkey_.p, 0xff, (size_t)cap * sizeof(unsigned long long), stream_));
     SAGE_CUDA(cudaMemsetAsync(tfirst_.p, 0xff, (size_t)cap * sizeof(uint32_t), stream_));
@@ -532,7 +563,9 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
     SAGE_LAUNCH(ds_flag_kernel, fe_blocks(n), kFeThreads, 0, stream_, slot_.p, tfirst_.p, flags_.p, (uint32_t)n);
     scan_flags(n, total_pin_.p, total_.p + 1);  // count and range-error flag land in pinned memory
     SAGE_LAUNCH(ds_collect_kernel, fe_blocks(n), kFeThreads, 0, stream_, slot_.p, flags_.p, pos_.p, tkey_.p, widx_.p, whash_pin_.p, (uint32_t)n);
+    const auto tr1 = fe_clock::now();
     SAGE_CUDA(cudaStreamSynchronize(stream_));
+    const auto tr2 = fe_clock::now();
     if (total_pin_.p[1]) throw ArgError("VoxelDownsample: point/voxel_size outside the +-2^19 voxel range");
     const size_t m = total_pin_.p[0];
     if (m == 0) return 0;
@@ -549,16 +582,24 @@ size_t FrontEnd::downsample(const double4 *in, size_t n, double vox_scale, const
         group_members_[g].push_back((uint32_t)j);
         group_hashes_[g].push_back(w & 0xfffffu);
     }
+    const auto tr3 = fe_clock::now();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(G < 6 ? G : 6) if (m > 1500)
     for (int g = 0; g < G; ++g) {
         group_order_[g].resize(group_members_[g].size());
         if (!group_members_[g].empty())
             robin_iteration_order(group_hashes_[g].data(), group_hashes_[g].size(), group_order_[g].data());
     }
+    const auto tr4 = fe_clock::now();
     size_t o = 0;
     for (int g = 0; g < G; ++g)
         for (size_t k = 0; k < group_order_[g].size(); ++k) perm_host[o++] = group_members_[g][group_order_[g][k]];
     SAGE_LAUNCH(ds_gather_kernel, fe_blocks(m), kFeThreads, 0, stream_, in, widx_.p, perm_host, crop, out, (uint32_t)m);
+    if (trace_) {
+        const auto tr5 = fe_clock::now();
+        auto sec = [](fe_clock::time_point a, fe_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        t_enqueue_ += sec(tr0, tr1), t_wait_ += sec(tr1, tr2), t_group_ += sec(tr2, tr3), t_replay_ += sec(tr3, tr4), t_tail_ += sec(tr4, tr5);
+        n_calls_ += 1, n_keys_ += (long long)m;
+    }
     return m;  // `out` is valid in stream order; callers that read it on the host synchronise themselves
 }
 
@@ -675,5 +716,11 @@ void FrontEnd::deskew(const double4 *in, const double *ts, size_t n, const Pose 
     pose_log(pose_mul(pose_inverse(start), finish), d);  // core/Deskew.cpp:40
     SAGE_LAUNCH(deskew_kernel, fe_blocks(n), kFeThreads, 0, stream_, in, ts, (uint32_t)n, d[0], d[1], d[2], d[3], d[4], d[5], out);
 }
+
+void preload_frontend_kernels() {
+    const void *ks[] = {(const void *)ds_insert_kernel, (const void *)ds_flag_kernel, (const void *)crop_flag_kernel, (const void *)crop_scatter_kernel, (const void *)ds_collect_kernel, (const void *)ds_gather_kernel, (const void *)scan_block_kernel, (const void *)scan_sums_kernel, (const void *)scan_add_kernel, (const void *)dyn_classify_kernel, (const void *)dyn_union_kernel, (const void *)dyn_size_kernel, (const void *)dyn_count_kernel, (const void *)dyn_flag_kernel, (const void *)dyn_scatter_kernel, (const void *)dyn_sortkey_kernel, (const void *)dyn_scatter_vehicle_kernel, (const void *)unpack_pointcloud2_kernel, (const void *)deskew_kernel, (const void *)occ_grid_kernel, (const void *)occ_overlap_kernel};
+    for (const void *k : ks) preload_kernel(k);
+}
+
 
 }  // namespace sage

@@ -87,6 +87,13 @@ private:
     DevBuf<int32_t> occ_;  // key-frame grids: current, last, two counters
     PinBuf<uint32_t> total_pin_, whash_pin_, perm_pin_[2];
     int parity_ = 0;
+    // SAGE_FE_TRACE=1: host-side time of VoxelDownsample by part, printed when the front end is destroyed (tools/stream_bench.py)
+    bool trace_ = false;
+    double t_enqueue_ = 0, t_wait_ = 0, t_group_ = 0, t_replay_ = 0, t_tail_ = 0;
+    long long n_calls_ = 0, n_keys_ = 0;
+public:
+    ~FrontEnd();
+private:
     std::vector<std::vector<uint32_t>> group_members_, group_hashes_, group_order_;
 };
 

@@ -22,6 +22,8 @@
 #include <cooperative_groups.h>
 
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 
 #include "nccl_shim.cuh"
@@ -1093,6 +1095,18 @@ static const void *tile_kernel_ptr(int minb, bool persistent) {
     }
 }
 
+void preload_registration_kernels() {
+    const void *ks[] = {(const void *)nn_search_kernel<false>, (const void *)nn_search_kernel<true>,
+                        (const void *)nn_search_persistent_kernel<1>, (const void *)nn_search_persistent_kernel<2>,
+                        (const void *)nn_search_persistent_kernel<SAGE_LIGHT_MINB>,
+                        (const void *)nn_tile_kernel<4>, (const void *)nn_tile_kernel<5>, (const void *)nn_tile_kernel<6>, (const void *)nn_tile_kernel<8>,
+                        (const void *)nn_tile_kernel<4, true>,
+                        (const void *)nn_tile_persistent_kernel<4>, (const void *)nn_tile_persistent_kernel<5>,
+                        (const void *)nn_tile_persistent_kernel<6>, (const void *)nn_tile_persistent_kernel<8>,
+                        (const void *)nn_stats_kernel, (const void *)icp_init_kernel, (const void *)icp_solve_kernel};
+    for (const void *k : ks) preload_kernel(k);
+}
+
 static long env_long(const char *name, long dflt) {
     const char *e = getenv(name);
     return e ? atol(e) : dflt;
@@ -1157,6 +1171,21 @@ void VoxelMapGPU::init_search_config() {
         xchg_timeout_ns_ = (unsigned long long)(t < 1 ? 1 : t) * 1000000000ull;
     }
     partials_.ensure((size_t)2 * kSums * (nn_grid_ > tile_grid_ ? nn_grid_ : tile_grid_));  // two buffers (iteration parity)
+    // The first COOPERATIVE launch of a kernel is slow even when its code is loaded (10-35 ms on B200: the driver sets the launch
+    // up per function), and which instantiation a registration needs depends on its query count — on a live drive that was a stall
+    // at the first frame with more than 1 184 queries.  So every persistent kernel is launched once here, on one block, with zero
+    // iterations (they leave at once and touch nothing).
+    if (coop_ok_) {
+        IterParams p = {};
+        int zero = 0;
+        void *args3[] = {&p, &zero, &zero};
+        const void *small[] = {(const void *)nn_search_persistent_kernel<1>, (const void *)nn_search_persistent_kernel<2>,
+                               (const void *)nn_search_persistent_kernel<SAGE_LIGHT_MINB>};
+        for (const void *k : small) SAGE_CUDA(cudaLaunchCooperativeKernel(k, dim3(1), dim3(kNnThreads), args3, 0, stream_));
+        void *args2[] = {&p, &zero};
+        SAGE_CUDA(cudaLaunchCooperativeKernel(k2, dim3(1), dim3(kTileThreads), args2, smem, stream_));
+        SAGE_CUDA(cudaStreamSynchronize(stream_));
+    }
 }
 
 // the rule by which nn_tile_iteration declines a query set (search_tile.cuh), for the paths that decide on the host
@@ -1317,10 +1346,14 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
         pose_out = guess;
         return 0;
     }
+    // SAGE_TRACE_SLOW=<ms>: a registration that takes longer says where the host spent the time (development aid)
+    static const double trace_slow_ms = getenv("SAGE_TRACE_SLOW") ? atof(getenv("SAGE_TRACE_SLOW")) : 0.0;
+    const auto tr0 = std::chrono::steady_clock::now();
     icp_.ensure(1);
     icp_pin_.ensure(1);
     src_.ensure(n ? n : 1);
     init_search_config();
+    const auto tr1 = std::chrono::steady_clock::now();
     // large scans: sort the queries by cell once, then the tile search (search_tile.cuh); the NCCL variant keeps its separate
     // all-reduce + solve launches, so it cannot run the loop in one launch
     bool tile = tile_min_ > 0 && n >= tile_min_;
@@ -1354,6 +1387,7 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
         launch_iteration(src_.p, n, max_dist, kernel, sem_th, 0, nullptr, nullptr, max_iters, 0, sorted);
         persistent = true;
     }
+    const auto tr2 = std::chrono::steady_clock::now();
     if (persistent) {
         SAGE_CUDA(cudaMemcpyAsync(icp_pin_.p, icp_.p, sizeof(IcpState), cudaMemcpyDeviceToHost, stream_));
         SAGE_CUDA(cudaStreamSynchronize(stream_));
@@ -1402,6 +1436,13 @@ int VoxelMapGPU::register_frame_dev(const double4 *frame, size_t n, const Pose &
         peer_detach();
         throw CudaError("peer exchange timed out: a rank of the sharded registration did not arrive; the peer communicator was detached, "
                         "re-attach on every rank (SAGE_XCHG_TIMEOUT_S sets the wait, default 30 s)");
+    }
+    if (trace_slow_ms > 0) {
+        const auto tr3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        if (ms(tr0, tr3) > trace_slow_ms)
+            fprintf(stderr, "[sage] slow registration: %zu queries, %d iterations, %.2f ms = buffers + configuration %.2f, enqueue %.2f, wait for the device %.2f\n",
+                    n, icp_pin_.p->iter, ms(tr0, tr3), ms(tr0, tr1), ms(tr1, tr2), ms(tr2, tr3));
     }
     pose_out = icp_pin_.p->result;
     last_iters_ = icp_pin_.p->iter;

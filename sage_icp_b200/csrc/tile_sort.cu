@@ -210,6 +210,13 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__rest
     for (uint32_t u = threadIdx.x; u < n_units; u += blockDim.x) order[atomicAdd(&s_bin[bin_of(u)], 1u)] = u;
 }
 
+void preload_tile_sort_kernels() {
+    const void *ks[] = {(const void *)tile_key_kernel, (const void *)tile_heads_kernel, (const void *)tile_gather_kernel,
+                        (const void *)tile_units_kernel, (const void *)tile_order_kernel};
+    for (const void *k : ks) preload_kernel(k);
+    // (the radix sort's kernels are CUB's: they load with the first scan of 12 288 queries or more)
+}
+
 // The kernels of tile_prepare, enqueued on stream_ (directly, or into a stream capture).  Every buffer is sized by the caller.
 int VoxelMapGPU::tile_prepare_enqueue(size_t n, bool with_init) {
     const uint32_t n32 = (uint32_t)n;

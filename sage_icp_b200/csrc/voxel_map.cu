@@ -307,6 +307,11 @@ static std::vector<int32_t> checked_labels(const int32_t *labels, int n) {
     return n ? std::vector<int32_t>(labels, labels + n) : std::vector<int32_t>();
 }
 
+void preload_voxel_map_kernels() {
+    const void *ks[] = {(const void *)tbl_clear_kernel, (const void *)tbl_reinsert_kernel, (const void *)ctrl_finish_kernel, (const void *)map_insert_keys_kernel, (const void *)map_link_kernel, (const void *)map_replay_kernel, (const void *)map_mark_first_kernel, (const void *)map_collect_new_kernel, (const void *)map_clear_new_kernel, (const void *)map_far_flags_kernel, (const void *)map_evict_list_kernel, (const void *)map_evict_kernel, (const void *)map_build_hot_kernel, (const void *)map_count_points_kernel, (const void *)ctrl_set_kernel};
+    for (const void *k : ks) preload_kernel(k);
+}
+
 VoxelMapGPU::VoxelMapGPU(double voxel_size, double max_distance, int basic, int critical, const int32_t *labels, int n_labels,
                          int device)
     : voxel_size_(voxel_size), max_distance_(max_distance), basic_(basic), critical_(critical), stride_(basic + critical),
@@ -322,6 +327,7 @@ VoxelMapGPU::VoxelMapGPU(double voxel_size, double max_distance, int basic, int 
     sm_count_ = prop.multiProcessorCount;
     set_device();
     SAGE_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    preload_voxel_map_kernels(), preload_registration_kernels(), preload_tile_sort_kernels();  // no first-use stalls mid-drive
     ctrl_.ensure(1);
     ctrl_pin_.ensure(1);
     icp_.ensure(1);

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--beams", type=int, default=64)
     ap.add_argument("--az", type=int, default=1875)
     ap.add_argument("--dynamic-filter", action="store_true", help="dynamic_vehicle_filter = true (ros/launch/odometry.launch.py:50)")
+    ap.add_argument("--pageable", action="store_true", help="hand the scans over in pageable memory, as the reference's node does (a std::vector)")
     a = ap.parse_args()
     import torch
     import sage_icp_b200 as sg
@@ -38,7 +39,7 @@ def main():
     for i in range(a.frames):
         scan = syn.make_scan(i, tuple(traj[i]), n_beams=a.beams, n_az=a.az)
         pin.copy_(torch.from_numpy(scan))
-        buf = pin.numpy()
+        buf = np.ascontiguousarray(scan) if a.pageable else pin.numpy()
         torch.cuda.synchronize()
         t = time.perf_counter()
         pg, t_icp, t_all = gp.register_frame(buf)
@@ -55,7 +56,7 @@ def main():
     g, c = np.array(t_gpu[warm:]), np.array(t_cpu[warm:])
     print(json.dumps({
         "workload": "BASELINE configs[2]: streaming RegisterFrame, synthetic KITTI-shaped drive, incremental Update on device",
-        "frames": a.frames, "dynamic_vehicle_filter": bool(a.dynamic_filter), "rays_per_scan": a.beams * a.az, "gpu_frames_per_s": float(1.0 / g.mean()), "gpu_ms_per_frame_median": float(1e3 * np.median(g)),
+        "frames": a.frames, "host_buffers": "pageable" if a.pageable else "pinned", "dynamic_vehicle_filter": bool(a.dynamic_filter), "rays_per_scan": a.beams * a.az, "gpu_frames_per_s": float(1.0 / g.mean()), "gpu_ms_per_frame_median": float(1e3 * np.median(g)),
         "gpu_ms_per_frame_p99": float(1e3 * np.percentile(g, 99)),
         "slowest_frames (index, ms)": [(int(i) + warm, round(float(1e3 * g[i]), 3)) for i in np.argsort(g)[-5:][::-1]], "mean_gn_iterations": float(np.mean(iters)),
         "mean_t_icp_ms": float(1e3 * np.mean(t_icps[warm:])), "mean_t_all_ms (front end + icp, reference meaning)": float(1e3 * np.mean(t_alls[warm:])), "mean_queries": float(np.mean(nsrc)),

@@ -35,12 +35,12 @@ size_t sort_pairs_tmp_bytes_u64(size_t n, int end_bit) {
 int sort_pairs_u32(void *tmp, size_t tmp_bytes, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *vals_in, uint32_t *vals_out, size_t n,
                    int end_bit, cudaStream_t stream) {
     SAGE_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, stream));
-    return 1 + (end_bit + 7) / 8;  // one histogram + one onesweep pass per 8-bit digit
+    return 2 + (end_bit + 7) / 8;  // histogram + exclusive sum + one onesweep pass per 8-bit digit (profiles/r02ah_launches.csv)
 }
 int sort_pairs_u64(void *tmp, size_t tmp_bytes, const unsigned long long *keys_in, unsigned long long *keys_out, const uint32_t *vals_in,
                    uint32_t *vals_out, size_t n, int end_bit, cudaStream_t stream) {
     SAGE_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, vals_in, vals_out, (int)n, 0, end_bit, stream));
-    return 1 + (end_bit + 7) / 8;
+    return 2 + (end_bit + 7) / 8;
 }
 
 // 8 bits for the horizontal cell axes (cells repeat every 256 cells = 410 m at 0.8 m voxels: twice the reach of a 100 m scan), 5 for

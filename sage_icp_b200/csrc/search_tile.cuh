@@ -33,8 +33,15 @@ constexpr int kTileThreads = 128;
 constexpr int kTileWarps = kTileThreads / 32;
 constexpr int kTileSlots = 2 * kTileThreads;  // region voxels per unit (two table probes per thread)
 constexpr int kTileCols = kTileThreads / 4;   // columns of a unit's sums (four threads share one, through two shuffles)
-constexpr int kTilePairs = 256;               // (query, bucket) pairs per pooled round
-constexpr int kTileGroup = 16;                // units per group of the two-level, fixed-order sum
+#ifndef SAGE_TILE_PAIRS
+#define SAGE_TILE_PAIRS 256
+#endif
+#ifndef SAGE_TILE_GROUP
+#define SAGE_TILE_GROUP 16
+#endif
+constexpr int kTilePairs = SAGE_TILE_PAIRS;   // (query, bucket) pairs per pooled round
+constexpr int kTileGroup = SAGE_TILE_GROUP;   // units per group of the two-level, fixed-order sum (tile_sort.cu sizes the counters for >= 16)
+static_assert(kTileGroup >= 16, "tile_prepare sizes the group counters for groups of at least 16 units");
 constexpr uint32_t kNotStaged = 0xffffffffu;
 static_assert(kTileCols == 32, "a unit's sums are reduced by one warp per sum");
 
@@ -127,6 +134,21 @@ __device__ __forceinline__ uint32_t tile_block_scan(TileShared &sh, uint32_t min
         total += sh.wsum[w];
     }
     return base;
+}
+
+// Sum k of a group: its units' partials added in unit order (the order is what makes the result reproducible).  The loads do not
+// depend on each other, so all of them are issued before the first addition: one trip to L2 instead of one per four units — the
+// last group of an iteration is summed on the iteration's critical path (measured: every unit more per group cost 0.28 us per
+// iteration, profiles/r02w_small_scans.md §9).
+__device__ __forceinline__ double tile_group_sum(const double *unit_part, uint32_t gfirst, uint32_t gsize, int k) {
+    double t[kTileGroup];
+#pragma unroll
+    for (int i = 0; i < kTileGroup; ++i) t[i] = (uint32_t)i < gsize ? __ldcg(&unit_part[(size_t)(gfirst + i) * kSums + k]) : 0.0;
+    double v = 0;
+#pragma unroll
+    for (int i = 0; i < kTileGroup; ++i)
+        if ((uint32_t)i < gsize) v += t[i];
+    return v;
 }
 
 // true (grid-uniformly) if this query set is left to the per-query kernel; sets the flag the host reads
@@ -525,11 +547,7 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
                 last = __shfl_sync(FULL, last, 0);
                 if (last) {
                     __threadfence();
-                    if (lane < kSums) {
-                        double v = 0;
-                        for (uint32_t i = gfirst; i < gfirst + gsize; ++i) v += __ldcg(&p.tile_unit_part[(size_t)i * kSums + lane]);
-                        group_partials[(size_t)lane * n_groups + g] = v;  // [sum][group]
-                    }
+                    if (lane < kSums) group_partials[(size_t)lane * n_groups + g] = tile_group_sum(p.tile_unit_part, gfirst, gsize, lane);  // [sum][group]
                     if (lane == 0) p.tile_group_cnt[g] = 0;  // ready for the next iteration
                 }
             }
@@ -555,9 +573,7 @@ __device__ __forceinline__ void nn_tile_iteration(const IterParams &p, TileShare
         if (sh.flag) {
             __threadfence();
             if (threadIdx.x < kSums) {
-                double v = 0;
-                for (uint32_t i = gfirst; i < gfirst + gsize; ++i) v += __ldcg(&p.tile_unit_part[(size_t)i * kSums + threadIdx.x]);
-                group_partials[(size_t)threadIdx.x * n_groups + g] = v;  // [sum][group]
+                group_partials[(size_t)threadIdx.x * n_groups + g] = tile_group_sum(p.tile_unit_part, gfirst, gsize, (int)threadIdx.x);  // [sum][group]
                 __threadfence();
             }
             __syncthreads();

@@ -1163,7 +1163,7 @@ void VoxelMapGPU::init_search_config() {
     if (env_long("SAGE_TILE", 1) == 0) tile_min_ = 0;
     tile_persistent_ = coop_ok_ && env_long("SAGE_TILE_PERSISTENT", 1) != 0;
     tile_by_size_ = env_long("SAGE_TILE_BY_SIZE", 1) != 0;
-    step_everywhere_ = (int)env_long("SAGE_STEP_EVERYWHERE", 1);  // 0 never, 1 where it pays (large tiled scans), 2 wherever possible
+    step_everywhere_ = (int)env_long("SAGE_STEP_EVERYWHERE", 1);  // 0 never, 1 where it pays (tile search; small scans on the wide instantiations), 2 wherever possible
     tile_fill_ = (size_t)env_long("SAGE_TILE_FILL", 1);  // 0: the tile search never declines a thinly spread query set
     tile_graph_ = env_long("SAGE_TILE_GRAPH", 1) != 0;   // sort + unit list replayed as a captured CUDA graph (tile_sort.cu)
     {

@@ -203,7 +203,7 @@ private:
     uint32_t tile_stage_cap_ = 0;  // staging area of a block, in 16-byte records
     bool tile_persistent_ = true;  // whole GN loop in one cooperative launch
     bool tile_by_size_ = true;     // hand the units out largest first
-    int step_everywhere_ = 1;      // persistent kernels, single rank: every block takes the Gauss-Newton step (0 never, 1 auto, 2 always)
+    int step_everywhere_ = 1;      // persistent kernels, single rank: every block takes the Gauss-Newton step (0 never, 1 where measured to pay, 2 always)
     size_t tile_fill_ = 1;         // 1: thinly spread query sets go to the per-query kernel (tile_units_too_thin); 0: never
     bool tile_units_too_thin(uint32_t n_units, size_t n) const;
     uint32_t last_units_ = 0;      // units of the last sorted scan
